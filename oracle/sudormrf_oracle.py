@@ -1,0 +1,361 @@
+"""CPU oracle for the SuDoRM-RF forward inference path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``sudo_rm_rf_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
+baseline / ``--impl reference`` legs use it, and only as the checker or the
+timed CPU baseline, never as the product path.
+
+It is a *functional restatement* (plain functions over a ``state_dict``; no
+``nn.Module``) of the reference's forward pass.  Citations are file:line in the
+reference tree (``/root/reference``):
+
+  improved_sudormrf.py   = sudo_rm_rf/dnn/models/improved_sudormrf.py
+  groupcomm_sudormrf_v2.py = sudo_rm_rf/dnn/models/groupcomm_sudormrf_v2.py
+  mixture_consistency.py = sudo_rm_rf/dnn/experiments/utils/mixture_consistency.py
+
+Parity pinning: the reference ships NO golden vectors for this path,
+so the oracle is pinned against outputs of the reference itself, generated in
+the build container by ``tests/golden/make_golden.py`` (which imports the
+unmodified reference from /root/reference) and committed as
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays them, and
+``tests/test_oracle_vs_reference.py`` compares live when /root/reference exists.
+
+All arithmetic is torch CPU, fp32 by default (the reference's dtype); pass
+``dtype=torch.float64`` for a high-precision run of the same formulas.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------
+# configuration
+# --------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Config:
+    """Constructor arguments of the two reference models.
+
+    improved_sudormrf.py:224-231 (SuDORMRF) and
+    groupcomm_sudormrf_v2.py:232-241 (GroupCommSudoRmRf).
+    """
+    variant: str = "improved"          # "improved" | "groupcomm"
+    out_channels: int = 128
+    in_channels: int = 512
+    num_blocks: int = 16
+    upsampling_depth: int = 4
+    enc_kernel_size: int = 21
+    enc_num_basis: int = 512
+    num_sources: int = 2
+    in_audio_channels: int = 1         # groupcomm only
+    group_size: int = 16               # groupcomm only
+
+    @property
+    def hop(self) -> int:
+        return self.enc_kernel_size // 2
+
+    @property
+    def n_least_samples_req(self) -> int:
+        # improved_sudormrf.py:244
+        return self.hop * 2 ** self.upsampling_depth
+
+    def as_dict(self):
+        return asdict(self)
+
+
+def padded_length(cfg: Config, T: int) -> int:
+    """improved_sudormrf.py:303-310: round T up to a multiple of hop*2^D
+    (at least one multiple)."""
+    q = cfg.n_least_samples_req
+    if T < q:
+        return q
+    return ((T + q - 1) // q) * q
+
+
+# --------------------------------------------------------------------------
+# parameter inventory (names/shapes are API: SURVEY §8 a1/a5/a8)
+# --------------------------------------------------------------------------
+def _ublock_shapes(prefix: str, co: int, ci: int, depth: int) -> Dict[str, tuple]:
+    # improved_sudormrf.py:170-196
+    s = {
+        f"{prefix}proj_1x1.conv.weight": (ci, co, 1),
+        f"{prefix}proj_1x1.conv.bias": (ci,),
+        f"{prefix}proj_1x1.norm.gamma": (ci,),
+        f"{prefix}proj_1x1.norm.beta": (ci,),
+        f"{prefix}proj_1x1.act.weight": (1,),
+    }
+    for d in range(depth):
+        s[f"{prefix}spp_dw.{d}.conv.weight"] = (ci, 1, 5)
+        s[f"{prefix}spp_dw.{d}.conv.bias"] = (ci,)
+        s[f"{prefix}spp_dw.{d}.norm.gamma"] = (ci,)
+        s[f"{prefix}spp_dw.{d}.norm.beta"] = (ci,)
+    s[f"{prefix}final_norm.norm.gamma"] = (ci,)
+    s[f"{prefix}final_norm.norm.beta"] = (ci,)
+    s[f"{prefix}final_norm.act.weight"] = (1,)
+    s[f"{prefix}res_conv.weight"] = (co, ci, 1)
+    s[f"{prefix}res_conv.bias"] = (co,)
+    return s
+
+
+def param_shapes(cfg: Config) -> Dict[str, tuple]:
+    """Ordered name -> shape map, in the reference's ``state_dict()`` order."""
+    N, Co, Ci = cfg.enc_num_basis, cfg.out_channels, cfg.in_channels
+    S, D, k = cfg.num_sources, cfg.upsampling_depth, cfg.enc_kernel_size
+    A = cfg.in_audio_channels if cfg.variant == "groupcomm" else 1
+    s: Dict[str, tuple] = {}
+    s["encoder.weight"] = (N, A, k)                  # improved_sudormrf.py:247-251
+    s["ln.gamma"] = (N,)
+    s["ln.beta"] = (N,)
+    s["bottleneck.weight"] = (Co, N, 1)
+    s["bottleneck.bias"] = (Co,)
+    for i in range(cfg.num_blocks):
+        if cfg.variant == "improved":
+            s.update(_ublock_shapes(f"sm.{i}.", Co, Ci, D))
+        else:
+            G = cfg.group_size
+            n, H = Co // G, Co * 3 // G              # groupcomm_sudormrf_v2.py:402
+            s[f"sm.{i}.TAC.TAC_input.0.weight"] = (H, n)
+            s[f"sm.{i}.TAC.TAC_input.0.bias"] = (H,)
+            s[f"sm.{i}.TAC.TAC_input.1.weight"] = (1,)
+            s[f"sm.{i}.TAC.TAC_mean.0.weight"] = (H, H)
+            s[f"sm.{i}.TAC.TAC_mean.0.bias"] = (H,)
+            s[f"sm.{i}.TAC.TAC_mean.1.weight"] = (1,)
+            s[f"sm.{i}.TAC.TAC_output.0.weight"] = (n, 2 * H)
+            s[f"sm.{i}.TAC.TAC_output.0.bias"] = (n,)
+            s[f"sm.{i}.TAC.TAC_output.1.weight"] = (1,)
+            s[f"sm.{i}.TAC.TAC_norm.gamma"] = (n,)
+            s[f"sm.{i}.TAC.TAC_norm.beta"] = (n,)
+            s.update(_ublock_shapes(f"sm.{i}.UBlock.", Co // G, Ci // G, D))
+    s["mask_net.0.weight"] = (1,)
+    s["mask_net.1.weight"] = (S * N * A, Co, 1)
+    s["mask_net.1.bias"] = (S * N * A,)
+    s["decoder.weight"] = (N * S * A, S * A, k)     # improved_sudormrf.py:272-279
+    return s
+
+
+def make_state_dict(cfg: Config, seed: int = 0, perturbed: bool = True,
+                    dtype=torch.float32) -> Dict[str, Tensor]:
+    """Seeded synthetic weights with the reference's names and shapes.
+
+    ``perturbed=True``: every parameter is non-trivial so that
+    gamma/beta/bias/PReLU slopes are exercised (the reference's default init has
+    gamma=1, beta=0, slope=.25 which hides bugs).  Matrices are scaled by
+    1/sqrt(fan_in) so activations stay O(1) through deep stacks.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    for name, shape in param_shapes(cfg).items():
+        if not perturbed:
+            if name.endswith("gamma"):
+                t = torch.ones(shape)
+            elif name.endswith("beta"):
+                t = torch.zeros(shape)
+            elif name.endswith("act.weight") or name in ("mask_net.0.weight",) or \
+                    (name.endswith(".1.weight") and "TAC" in name):
+                t = torch.full(shape, 0.25)
+            else:
+                fan_in = max(1, int(math.prod(shape[1:])))
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        else:
+            if name.endswith("gamma"):
+                t = 1.0 + 0.3 * torch.randn(shape, generator=g)
+            elif name.endswith("beta"):
+                t = 0.2 * torch.randn(shape, generator=g)
+            elif len(shape) == 1 and shape[0] == 1:
+                t = 0.25 + 0.15 * torch.rand(shape, generator=g)   # PReLU slopes
+            elif len(shape) == 1:
+                t = 0.1 * torch.randn(shape, generator=g)          # biases
+            else:
+                fan_in = max(1, int(math.prod(shape[1:])))
+                t = torch.randn(shape, generator=g) * (1.0 / math.sqrt(fan_in))
+        sd[name] = t.to(dtype)
+    return sd
+
+
+# --------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------
+def glob_ln(x: Tensor, gamma: Tensor, beta: Tensor) -> Tensor:
+    """Global layer norm, improved_sudormrf.py:30-47: biased two-pass variance
+    over every non-batch dim, eps=1e-8 inside the sqrt, per-channel affine."""
+    dims = tuple(range(1, x.dim()))
+    mu = x.mean(dim=dims, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=dims, keepdim=True)
+    xn = (x - mu) / torch.sqrt(var + 1e-8)
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    return xn * gamma.view(shape) + beta.view(shape)
+
+
+def prelu1(x: Tensor, slope: Tensor) -> Tensor:
+    """nn.PReLU() with its single shared slope (improved_sudormrf.py:68,111)."""
+    return torch.where(x >= 0, x, x * slope.reshape(()))
+
+
+def pad_wave(cfg: Config, wav: Tensor, dtype) -> Tensor:
+    """improved_sudormrf.py:303-314: zero-pad on the right to padded_length;
+    the reference materialises the pad in fp32."""
+    T = wav.shape[-1]
+    Tp = padded_length(cfg, T)
+    out = torch.zeros(list(wav.shape[:-1]) + [Tp], dtype=dtype)
+    out[..., :T] = wav.to(dtype)
+    return out
+
+
+def uconv_block(x: Tensor, sd: Dict[str, Tensor], p: str, depth: int,
+                taps: Optional[dict] = None) -> Tensor:
+    """One U-ConvBlock, improved_sudormrf.py:198-220.
+
+    y   = PReLU(GLN(W1 x + b1))                               (:205, ConvNormAct :70-73)
+    z_0 = GLN(dw5_s1(y)), z_d = GLN(dw5_s2(z_{d-1}))          (:206-211)
+    m   = z_0 + up2(z_1 + up2(z_2 + ...))  (nearest)          (:214-216)
+    out = W2 PReLU(GLN(m)) + b2 + x                           (:218-220)
+    """
+    ci = sd[p + "proj_1x1.conv.weight"].shape[0]
+    y = F.conv1d(x, sd[p + "proj_1x1.conv.weight"], sd[p + "proj_1x1.conv.bias"])
+    if taps is not None:
+        taps[p + "proj_1x1.conv"] = y
+    y = glob_ln(y, sd[p + "proj_1x1.norm.gamma"], sd[p + "proj_1x1.norm.beta"])
+    y = prelu1(y, sd[p + "proj_1x1.act.weight"])
+    levels = []
+    cur = y
+    for d in range(depth):
+        stride = 1 if d == 0 else 2                             # :181-189
+        z = F.conv1d(cur, sd[p + f"spp_dw.{d}.conv.weight"],
+                     sd[p + f"spp_dw.{d}.conv.bias"],
+                     stride=stride, padding=2, groups=ci)
+        if taps is not None:
+            taps[p + f"spp_dw.{d}.conv"] = z
+        cur = glob_ln(z, sd[p + f"spp_dw.{d}.norm.gamma"],
+                      sd[p + f"spp_dw.{d}.norm.beta"])
+        levels.append(cur)
+    for _ in range(depth - 1):
+        top = levels.pop()
+        levels[-1] = levels[-1] + F.interpolate(top, scale_factor=2, mode="nearest")
+    m = levels[0]
+    if taps is not None:
+        taps[p + "merge"] = m
+    e = glob_ln(m, sd[p + "final_norm.norm.gamma"], sd[p + "final_norm.norm.beta"])
+    e = prelu1(e, sd[p + "final_norm.act.weight"])
+    out = F.conv1d(e, sd[p + "res_conv.weight"], sd[p + "res_conv.bias"]) + x
+    if taps is not None:
+        taps[p + "out"] = out
+    return out
+
+
+def tac(x4: Tensor, sd: Dict[str, Tensor], p: str,
+        taps: Optional[dict] = None) -> Tensor:
+    """Transform-average-concatenate, groupcomm_sudormrf_v2.py:356-384.
+
+    x4: [B, G, n, L].  Per (b, t): h_g = PReLU(W1 x_g + b1); mean over groups;
+    q = PReLU(W2 mean + b2); o_g = PReLU(W3 [h_g; q] + b3); then GlobLN over
+    (n, L) per (b, g) and a residual add.
+    """
+    B, G, n, L = x4.shape
+    xin = x4.permute(0, 3, 1, 2).reshape(B * L * G, n)
+    h = prelu1(F.linear(xin, sd[p + "TAC_input.0.weight"], sd[p + "TAC_input.0.bias"]),
+               sd[p + "TAC_input.1.weight"]).view(B, L, G, -1)
+    mean = h.mean(2).reshape(B * L, -1)
+    q = prelu1(F.linear(mean, sd[p + "TAC_mean.0.weight"], sd[p + "TAC_mean.0.bias"]),
+               sd[p + "TAC_mean.1.weight"])
+    q = q.unsqueeze(1).expand(B * L, G, q.shape[-1])
+    cat = torch.cat([h.view(B * L, G, -1), q], dim=2).reshape(B * L * G, -1)
+    o = prelu1(F.linear(cat, sd[p + "TAC_output.0.weight"], sd[p + "TAC_output.0.bias"]),
+               sd[p + "TAC_output.1.weight"])
+    o = o.view(B, L, G, n).permute(0, 2, 3, 1).contiguous()      # B, G, n, L
+    if taps is not None:
+        taps[p + "TAC_output"] = o
+    o = glob_ln(o.view(B * G, n, L), sd[p + "TAC_norm.gamma"], sd[p + "TAC_norm.beta"])
+    return x4 + o.view(B, G, n, L)
+
+
+def gc_uconv_block(x: Tensor, sd: Dict[str, Tensor], p: str, depth: int, G: int,
+                   taps: Optional[dict] = None) -> Tensor:
+    """groupcomm_sudormrf_v2.py:405-418: TAC over the group view, then ONE small
+    U-ConvBlock shared by all groups, groups folded into the batch."""
+    B, C, L = x.shape
+    t = tac(x.view(B, G, C // G, L), sd, p + "TAC.", taps)
+    if taps is not None:
+        taps[p + "TAC"] = t.reshape(B, C, L)
+    y = uconv_block(t.reshape(B * G, C // G, L), sd, p + "UBlock.", depth, taps)
+    return y.view(B, C, L)
+
+
+# --------------------------------------------------------------------------
+# whole-model forwards
+# --------------------------------------------------------------------------
+def forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor,
+            taps: Optional[dict] = None, dtype=torch.float32) -> Tensor:
+    """SuDORMRF.forward (improved_sudormrf.py:283-301) /
+    GroupCommSudoRmRf.forward (groupcomm_sudormrf_v2.py:302-322).
+
+    wav: [B, A, T] (A = 1, or in_audio_channels for groupcomm) -> [B, S*A, T].
+    """
+    if wav.dim() != 3:
+        raise RuntimeError("expected a 3-D input [batch, audio_channels, time]")
+    sd = {k: v.to(dtype) for k, v in sd.items()}
+    T = wav.shape[-1]
+    k, hop = cfg.enc_kernel_size, cfg.hop
+    S, N = cfg.num_sources, cfg.enc_num_basis
+    A = cfg.in_audio_channels if cfg.variant == "groupcomm" else 1
+    x = pad_wave(cfg, wav, dtype)
+    x = F.conv1d(x, sd["encoder.weight"], None, stride=hop, padding=hop)   # :286
+    if taps is not None:
+        taps["encoder"] = x
+    s = x                                                                   # :289
+    x = glob_ln(x, sd["ln.gamma"], sd["ln.beta"])                           # :291
+    x = F.conv1d(x, sd["bottleneck.weight"], sd["bottleneck.bias"])         # :292
+    if taps is not None:
+        taps["bottleneck"] = x
+    for i in range(cfg.num_blocks):                                         # :293
+        if cfg.variant == "improved":
+            x = uconv_block(x, sd, f"sm.{i}.", cfg.upsampling_depth, taps)
+        else:
+            x = gc_uconv_block(x, sd, f"sm.{i}.", cfg.upsampling_depth,
+                               cfg.group_size, taps)
+    x = prelu1(x, sd["mask_net.0.weight"])                                  # :295
+    x = F.conv1d(x, sd["mask_net.1.weight"], sd["mask_net.1.bias"])
+    x = x.view(x.shape[0], S * A, N, -1)                                    # :296
+    x = torch.relu(x) * s.unsqueeze(1)                                      # :297-298
+    if taps is not None:
+        taps["masked"] = x.reshape(x.shape[0], -1, x.shape[-1])
+    y = F.conv_transpose1d(x.reshape(x.shape[0], -1, x.shape[-1]),
+                           sd["decoder.weight"], None, stride=hop, padding=hop,
+                           output_padding=hop - 1)                          # :300
+    return y[..., :T]                                                       # :301
+
+
+def mixture_consistency(est: Tensor, mix: Tensor,
+                        mix_weights_type: str = "uniform") -> Tensor:
+    """mixture_consistency.py:14-36."""
+    S = est.shape[1]
+    resid = mix - est.sum(1, keepdim=True)
+    if mix_weights_type == "uniform":
+        w = 1.0 / S
+    elif mix_weights_type == "magsq":
+        w = (est ** 2).mean(-1, keepdim=True)
+        w = w / (w.sum(1, keepdim=True) + 1e-9)
+    else:
+        raise ValueError(
+            "Invalid mixture consistency weight type: {}".format(mix_weights_type))
+    return est + w * resid
+
+
+# --------------------------------------------------------------------------
+# tolerance used by every parity test
+# --------------------------------------------------------------------------
+def parity_errors(y: Tensor, ref: Tensor):
+    """Returns (max over samples of max|y-ref|/max|ref|, rel-L2)."""
+    y = y.double().cpu()
+    ref = ref.double().cpu()
+    B = ref.shape[0]
+    d = (y - ref).reshape(B, -1).abs().amax(1)
+    m = ref.reshape(B, -1).abs().amax(1).clamp_min(1e-30)
+    rel_max = float((d / m).max())
+    rel_l2 = float((y - ref).norm() / ref.norm().clamp_min(1e-30))
+    return rel_max, rel_l2
