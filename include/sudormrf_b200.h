@@ -1,0 +1,174 @@
+/*
+ * sudormrf_b200.h — C ABI of the B200-native SuDoRM-RF forward path.
+ *
+ * The reference (etzinis/sudo_rm_rf) has no native/FFI layer: its boundary is
+ * the Python nn.Module contract.  This header is the C-ABI that sits UNDER the
+ * Python mirror of that contract (sudo_rm_rf_b200/improved_sudormrf.py etc.);
+ * each entry point names the reference interface it replaces (file:line in
+ * /root/reference).  Plain pointers and sizes only; no torch types.
+ *
+ * Ownership: the caller owns every byte (parameters, packed weights,
+ * workspace, inputs, outputs are caller-allocated device buffers); the library
+ * never allocates or frees device memory and keeps no mutable global state
+ * beyond one-time cudaFuncSetAttribute calls.  All work is enqueued on the
+ * stream passed in; nothing synchronises.  Fully re-entrant (nn.DataParallel
+ * calls forward from one host thread per device).
+ *
+ * Errors: integer return codes, 0 = OK, negative = failure (see
+ * sdr_error_string).  No C++ exceptions cross the ABI.
+ */
+#ifndef SUDORMRF_B200_H
+#define SUDORMRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDR_ABI_VERSION 1
+
+/* return codes */
+#define SDR_OK                 0
+#define SDR_ERR_BAD_CONFIG    -1   /* constructor arguments the kernels cannot run */
+#define SDR_ERR_BAD_ARGUMENT  -2   /* null pointer, wrong count, B/T <= 0 ... */
+#define SDR_ERR_WORKSPACE     -3   /* workspace / packed buffer too small */
+#define SDR_ERR_CUDA          -4   /* a CUDA call or launch failed */
+#define SDR_ERR_UNSUPPORTED   -5   /* valid for the reference, not implemented here */
+
+/* Constructor arguments of the two reference models:
+ *   improved_sudormrf.py:224-231   SuDORMRF.__init__
+ *   groupcomm_sudormrf_v2.py:232-241 GroupCommSudoRmRf.__init__            */
+typedef struct {
+    int32_t variant;            /* 0 = improved SuDORMRF, 1 = GroupCommSudoRmRf */
+    int32_t in_audio_channels;  /* 1 for improved */
+    int32_t out_channels;
+    int32_t in_channels;
+    int32_t num_blocks;
+    int32_t upsampling_depth;
+    int32_t enc_kernel_size;
+    int32_t enc_num_basis;
+    int32_t num_sources;
+    int32_t group_size;         /* ignored for improved */
+} sdr_config;
+
+typedef void* sdr_stream;       /* a cudaStream_t (CUstream); NULL = legacy default stream */
+
+int         sdr_abi_version(void);
+const char* sdr_error_string(int code);
+
+/* Number of parameter tensors in the reference's state_dict() order
+ * (improved_sudormrf.py:247-281, :170-196; groupcomm_sudormrf_v2.py:262-299,
+ * :347-354, :401-403) and the element count of parameter i.                 */
+int     sdr_num_params(const sdr_config* cfg);
+int64_t sdr_param_numel(const sdr_config* cfg, int index);
+
+/* Padded length rule of pad_to_appropriate_length (improved_sudormrf.py:303-310). */
+int64_t sdr_padded_length(const sdr_config* cfg, int64_t T);
+
+/* Packed weights: one flat device buffer holding every parameter plus derived
+ * layouts (decoder weight as a [S*K, S*N] matrix, ...).  A single buffer so the
+ * multi-GPU driver can broadcast it with ONE ncclBroadcast.  Replaces the
+ * per-forward module replication of nn.DataParallel
+ * (run_improved_sudormrf.py:118).                                            */
+size_t sdr_packed_weight_bytes(const sdr_config* cfg);
+int    sdr_pack_weights(const sdr_config* cfg,
+                        const float* const* params, /* host array of n device pointers, state_dict order, fp32 contiguous */
+                        int n_params,
+                        void* packed, size_t packed_bytes, sdr_stream stream);
+
+/* Caller-allocated scratch for a forward at batch B, length T (all
+ * intermediates + the GlobLN statistics).                                    */
+size_t sdr_workspace_bytes(const sdr_config* cfg, int B, int64_t T);
+
+/* SuDORMRF.forward (improved_sudormrf.py:283-301) /
+ * GroupCommSudoRmRf.forward (groupcomm_sudormrf_v2.py:302-322), optionally
+ * followed by mixture_consistency.apply(..., 'uniform')
+ * (mixture_consistency.py:14-36; only when in_audio_channels == 1).
+ *   mixture: device [B, in_audio_channels, T] fp32 contiguous
+ *   out:     device [B, num_sources*in_audio_channels, T] fp32 contiguous   */
+int sdr_forward(const sdr_config* cfg, const void* packed,
+                const float* mixture, float* out, int B, int64_t T,
+                int apply_mixture_consistency,
+                void* workspace, size_t workspace_bytes, sdr_stream stream);
+
+/* Number of kernels one sdr_forward enqueues (the benchmark's gpu_launches claim). */
+int sdr_forward_launch_count(const sdr_config* cfg);
+
+/* Same call with HOST buffers (pinned for real asynchrony): H2D copy of the
+ * mixture, forward, D2H copy of the estimates, all on `stream`.  `dev_io` is a
+ * device staging buffer of sdr_host_staging_bytes().  This is the end-to-end
+ * entry the benchmark's `e2e` figure times.                                  */
+size_t sdr_host_staging_bytes(const sdr_config* cfg, int B, int64_t T);
+int sdr_forward_host(const sdr_config* cfg, const void* packed,
+                     const float* host_mixture, float* host_out, int B, int64_t T,
+                     int apply_mixture_consistency,
+                     void* dev_io, size_t dev_io_bytes,
+                     void* workspace, size_t workspace_bytes, sdr_stream stream);
+
+/* mixture_consistency.apply (mixture_consistency.py:14-36).
+ * weights_type: 0 = 'uniform', 1 = 'magsq'.  est/out [B,S,T], mix [B,1,T].
+ * `scratch` (device, >= B*S doubles) is only used by 'magsq'.               */
+int sdr_mixture_consistency(const float* est, const float* mix, float* out,
+                            int B, int S, int64_t T, int weights_type,
+                            void* scratch, sdr_stream stream);
+
+/* ---- per-stage entry points (stage-level parity tests; same kernels the
+ *      forward launches).  "Deferred GlobLN": a producer stores its RAW output
+ *      and accumulates per-sample (sum, sum of squares) in fp64 into `stats`
+ *      ([samples][2] doubles, zero-initialised by the caller); the consumer
+ *      applies gamma*(x-mean)*rstd+beta (+PReLU) while loading.
+ *      GlobLN = improved_sudormrf.py:30-47.                                  */
+
+/* description of a deferred normalisation applied to an input while loading */
+typedef struct {
+    const double* stats;   /* [samples][2] or NULL = no normalisation */
+    const float*  gamma;   /* [C] */
+    const float*  beta;    /* [C] */
+    const float*  prelu;   /* 1 element, or NULL = no activation */
+    double        count;   /* elements per sample the statistics were taken over */
+} sdr_norm_in;
+
+/* nn.Conv1d(A, N, k, stride=k/2, padding=k/2, bias=False) on the zero-padded
+ * waveform (improved_sudormrf.py:247-251,286,303-314).
+ * wav [B,A,T] -> enc [B,N,L] (L = padded_length/hop), stats over (N,L).      */
+int sdr_encoder(const float* wav, const float* weight, float* enc, double* stats,
+                int B, int A, int64_t T, int N, int K, int L, sdr_stream stream);
+
+/* 1x1 Conv1d as a GEMM: y[b,m,l] = sum_k W[m,k] f(x[b,k,l]) + bias[m]
+ * (+ residual[b,m,l]); f = deferred norm/PReLU.  epilogue 0: plain,
+ * 1: relu(y) * gate[b, m % gate_channels, l] (mask path, improved_sudormrf.py:296-298).
+ * Replaces bottleneck / proj_1x1.conv / res_conv / mask_net.1 (+decoder GEMM). */
+int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const float* bias,
+                  const float* residual, const float* gate, int gate_channels,
+                  float* y, double* stats_out,
+                  int samples, int M, int Kc, int L, int epilogue, sdr_stream stream);
+
+/* depthwise Conv1d(k=5, padding=2, stride 1|2, groups=C) on the deferred-normalised
+ * input (improved_sudormrf.py:178-189,206-211).  x [samples,C,Lin] ->
+ * y [samples,C,Lout] raw + stats.                                            */
+int sdr_depthwise(const float* x, const sdr_norm_in* fin, const float* w5, const float* bias,
+                  float* y, double* stats_out,
+                  int samples, int C, int Lin, int stride, sdr_stream stream);
+
+/* nearest x2 up-sampling + skip adds, closed form
+ * m[c,t] = sum_d norm_d(z_d)[c, t>>d] (improved_sudormrf.py:214-216).        */
+int sdr_merge(const float* const* z, const sdr_norm_in* fins, int depth,
+              float* m, double* stats_out, int samples, int C, int L, sdr_stream stream);
+
+/* TAC (groupcomm_sudormrf_v2.py:356-384) up to (not including) its GlobLN:
+ * x [B,G,n,L] -> o [B,G,n,L] raw + stats per (b,g).  params = the 9 TAC
+ * tensors before TAC_norm, state_dict order.                                 */
+int sdr_tac(const float* x, const float* const* params, float* o, double* stats_out,
+            int B, int G, int n, int L, sdr_stream stream);
+
+/* ConvTranspose1d overlap-add + crop (+ uniform mixture consistency):
+ * frames [B, SA*K, L] -> out [B, SA, T] (improved_sudormrf.py:272-279,300-301). */
+int sdr_overlap_add(const float* frames, const float* mix_or_null, float* out,
+                    int B, int SA, int K, int L, int64_t T, sdr_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUDORMRF_B200_H */

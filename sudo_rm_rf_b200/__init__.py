@@ -1,0 +1,12 @@
+"""sudo_rm_rf_b200: B200-native (sm_100a) forward inference path of SuDoRM-RF.
+
+Mirrors ``sudo_rm_rf.dnn.models.improved_sudormrf`` /
+``sudo_rm_rf.dnn.models.groupcomm_sudormrf_v2`` /
+``sudo_rm_rf.dnn.experiments.utils.mixture_consistency`` of etzinis/sudo_rm_rf.
+"""
+from . import improved_sudormrf, groupcomm_sudormrf_v2, mixture_consistency   # noqa: F401
+from .improved_sudormrf import SuDORMRF                                       # noqa: F401
+from .groupcomm_sudormrf_v2 import GroupCommSudoRmRf                          # noqa: F401
+
+__all__ = ["SuDORMRF", "GroupCommSudoRmRf", "improved_sudormrf", "groupcomm_sudormrf_v2",
+           "mixture_consistency"]

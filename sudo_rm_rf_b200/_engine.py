@@ -1,0 +1,219 @@
+"""Host-side glue between the ``nn.Module`` mirrors and the C-ABI.
+
+PyTorch is used here only as plumbing: it owns device memory (parameters,
+packed weights, workspace, outputs come from its caching allocator) and names
+the CUDA stream the kernels are enqueued on.  All arithmetic happens in
+``libsudormrf_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import List
+
+import torch
+
+from . import _native as N
+
+_tls_lock = threading.Lock()
+
+
+def make_config(model) -> N.SdrConfig:
+    """Constructor arguments -> ``sdr_config``; reads the public attributes the
+    reference stores (improved_sudormrf.py:235-241, groupcomm_sudormrf_v2.py:245-252)."""
+    gc = hasattr(model, "in_audio_channels")
+    group = 1
+    if gc:
+        group = int(getattr(model, "group_size", 0) or
+                    (model.sm[0].num_group if len(model.sm) else 16))
+    return N.SdrConfig(
+        variant=1 if gc else 0,
+        in_audio_channels=int(getattr(model, "in_audio_channels", 1)),
+        out_channels=int(model.out_channels), in_channels=int(model.in_channels),
+        num_blocks=int(model.num_blocks), upsampling_depth=int(model.upsampling_depth),
+        enc_kernel_size=int(model.enc_kernel_size), enc_num_basis=int(model.enc_num_basis),
+        num_sources=int(model.num_sources), group_size=group)
+
+
+def state_dict_names(cfg: N.SdrConfig) -> List[str]:
+    """Parameter names in the reference's ``state_dict()`` order
+    (improved_sudormrf.py:247-281,170-196; groupcomm_sudormrf_v2.py:347-354,401-403)."""
+    names = ["encoder.weight", "ln.gamma", "ln.beta", "bottleneck.weight", "bottleneck.bias"]
+
+    def ublock(p):
+        out = [p + "proj_1x1.conv.weight", p + "proj_1x1.conv.bias", p + "proj_1x1.norm.gamma",
+               p + "proj_1x1.norm.beta", p + "proj_1x1.act.weight"]
+        for d in range(cfg.upsampling_depth):
+            out += [p + f"spp_dw.{d}.conv.weight", p + f"spp_dw.{d}.conv.bias",
+                    p + f"spp_dw.{d}.norm.gamma", p + f"spp_dw.{d}.norm.beta"]
+        out += [p + "final_norm.norm.gamma", p + "final_norm.norm.beta",
+                p + "final_norm.act.weight", p + "res_conv.weight", p + "res_conv.bias"]
+        return out
+
+    for i in range(cfg.num_blocks):
+        if cfg.variant == 0:
+            names += ublock(f"sm.{i}.")
+        else:
+            t = f"sm.{i}.TAC."
+            names += [t + "TAC_input.0.weight", t + "TAC_input.0.bias", t + "TAC_input.1.weight",
+                      t + "TAC_mean.0.weight", t + "TAC_mean.0.bias", t + "TAC_mean.1.weight",
+                      t + "TAC_output.0.weight", t + "TAC_output.0.bias", t + "TAC_output.1.weight",
+                      t + "TAC_norm.gamma", t + "TAC_norm.beta"]
+            names += ublock(f"sm.{i}.UBlock.")
+    names += ["mask_net.0.weight", "mask_net.1.weight", "mask_net.1.bias", "decoder.weight"]
+    return names
+
+
+def _fetch(model, dotted: str) -> torch.Tensor:
+    # attribute walk (not named_parameters): nn.DataParallel replicas hold plain
+    # tensors in _parameters and report no parameters()
+    obj = model
+    for part in dotted.split("."):
+        obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+    return obj
+
+
+class _DeviceState:
+    """Per (model, device) cache: packed weights + workspace."""
+    __slots__ = ("sig", "packed", "workspace", "staging")
+
+    def __init__(self):
+        self.sig = None
+        self.packed = None
+        self.workspace = None
+        self.staging = None
+
+
+def _state(model, device) -> _DeviceState:
+    cache = model.__dict__.get("_b200_cache")
+    if cache is None:
+        with _tls_lock:
+            cache = model.__dict__.setdefault("_b200_cache", {})
+    st = cache.get(device.index)
+    if st is None:
+        st = cache.setdefault(device.index, _DeviceState())
+    return st
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def packed_weights(model, cfg: N.SdrConfig, device) -> torch.Tensor:
+    """Flat packed-weight buffer for ``model`` on ``device`` (re-packed whenever a
+    parameter's storage or version counter changes)."""
+    lib = N.lib()
+    st = _state(model, device)
+    names = state_dict_names(cfg)
+    tensors = [_fetch(model, n) for n in names]
+    sig = tuple((t.data_ptr(), t._version) for t in tensors)
+    if st.sig == sig and st.packed is not None:
+        return st.packed
+    n = lib.sdr_num_params(C.byref(cfg))
+    if n < 0:
+        N.check(n, "sdr_num_params")
+    if n != len(tensors):
+        raise N.NativeError(f"parameter inventory mismatch: library expects {n}, module has {len(tensors)}")
+    flat = []
+    for i, (name, t) in enumerate(zip(names, tensors)):
+        if t.device != device:
+            raise RuntimeError(f"parameter {name} is on {t.device}, input is on {device}")
+        want = lib.sdr_param_numel(C.byref(cfg), i)
+        if t.numel() != want:
+            raise RuntimeError(f"parameter {name} has {t.numel()} elements, expected {want}")
+        flat.append(t.detach().to(torch.float32).contiguous())
+    nbytes = lib.sdr_packed_weight_bytes(C.byref(cfg))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ptrs = (C.c_void_p * n)(*[C.c_void_p(t.data_ptr()) for t in flat])
+    N.check(lib.sdr_pack_weights(C.byref(cfg), ptrs, n, C.c_void_p(packed.data_ptr()), nbytes,
+                                 _stream_ptr(device)), "sdr_pack_weights")
+    st.sig, st.packed = sig, packed
+    return packed
+
+
+def _check_input(model, cfg, wav: torch.Tensor) -> torch.Tensor:
+    if wav.dim() != 3:
+        raise RuntimeError(
+            f"Expected 3D input [batch, channels, time] to the encoder, got {list(wav.shape)}")
+    if wav.shape[1] != cfg.in_audio_channels:
+        raise RuntimeError(f"expected {cfg.in_audio_channels} audio channel(s), got {wav.shape[1]}")
+    if not wav.is_cuda:
+        raise RuntimeError(
+            "sudo_rm_rf_b200 runs on CUDA (sm_100a) only and has no CPU path: move the model "
+            "and the mixture to a B200 (`model.cuda()`, `mixture.cuda()`).")
+    if torch.is_grad_enabled() and model.training and \
+            any(_fetch(model, n).requires_grad for n in ("encoder.weight", "decoder.weight")):
+        raise RuntimeError(
+            "sudo_rm_rf_b200 implements the inference forward only (no autograd): call "
+            "model.eval() and/or wrap the call in torch.no_grad().")
+    if wav.shape[0] == 0 or wav.shape[-1] == 0:
+        raise RuntimeError("empty batch or zero-length mixture")
+    # the reference casts to fp32 while padding (improved_sudormrf.py:312)
+    return wav.detach().to(torch.float32).contiguous()
+
+
+def forward(model, wav: torch.Tensor, mixture_consistency: bool = False) -> torch.Tensor:
+    """``model(wav)`` on the native path.  [B, A, T] -> [B, S*A, T] fp32, same device."""
+    lib = N.lib()
+    cfg = make_config(model)
+    x = _check_input(model, cfg, wav)
+    device = x.device
+    B, _, T = x.shape
+    with torch.cuda.device(device):
+        packed = packed_weights(model, cfg, device)
+        st = _state(model, device)
+        ws_bytes = lib.sdr_workspace_bytes(C.byref(cfg), B, T)
+        if ws_bytes == 0:
+            raise N.NativeError("bad model configuration (sdr_workspace_bytes returned 0)")
+        if st.workspace is None or st.workspace.numel() < ws_bytes:
+            st.workspace = None
+            st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        out = torch.empty((B, cfg.num_sources * cfg.in_audio_channels, T),
+                          dtype=torch.float32, device=device)
+        N.check(lib.sdr_forward(C.byref(cfg), C.c_void_p(packed.data_ptr()),
+                                C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                B, T, 1 if mixture_consistency else 0,
+                                C.c_void_p(st.workspace.data_ptr()), st.workspace.numel(),
+                                _stream_ptr(device)), "sdr_forward")
+    return out
+
+
+def forward_host(model, host_wav: torch.Tensor, host_out: torch.Tensor = None,
+                 mixture_consistency: bool = False, device=None) -> torch.Tensor:
+    """End-to-end call with HOST buffers (pinned for asynchrony): H2D copy,
+    forward, D2H copy, all enqueued on the current stream of the model's device.
+    The caller synchronises the stream before reading ``host_out``."""
+    lib = N.lib()
+    cfg = make_config(model)
+    if host_wav.dim() != 3 or host_wav.is_cuda or host_wav.dtype != torch.float32 \
+            or not host_wav.is_contiguous():
+        raise RuntimeError("forward_host expects a contiguous fp32 CPU tensor [B, A, T]")
+    device = torch.device(device) if device is not None else _fetch(model, "encoder.weight").device
+    if device.type != "cuda":
+        raise RuntimeError("the model must live on a CUDA device")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    B, A, T = host_wav.shape
+    if A != cfg.in_audio_channels:
+        raise RuntimeError(f"expected {cfg.in_audio_channels} audio channel(s), got {A}")
+    if host_out is None:
+        host_out = torch.empty((B, cfg.num_sources * A, T), dtype=torch.float32).pin_memory()
+    with torch.cuda.device(device):
+        packed = packed_weights(model, cfg, device)
+        st = _state(model, device)
+        ws_bytes = lib.sdr_workspace_bytes(C.byref(cfg), B, T)
+        io_bytes = lib.sdr_host_staging_bytes(C.byref(cfg), B, T)
+        if ws_bytes == 0 or io_bytes == 0:
+            raise N.NativeError("bad model configuration")
+        if st.workspace is None or st.workspace.numel() < ws_bytes:
+            st.workspace = None
+            st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        if st.staging is None or st.staging.numel() < io_bytes:
+            st.staging = torch.empty(io_bytes, dtype=torch.uint8, device=device)
+        N.check(lib.sdr_forward_host(C.byref(cfg), C.c_void_p(packed.data_ptr()),
+                                     C.c_void_p(host_wav.data_ptr()), C.c_void_p(host_out.data_ptr()),
+                                     B, T, 1 if mixture_consistency else 0,
+                                     C.c_void_p(st.staging.data_ptr()), st.staging.numel(),
+                                     C.c_void_p(st.workspace.data_ptr()), st.workspace.numel(),
+                                     _stream_ptr(device)), "sdr_forward_host")
+    return host_out

@@ -1,0 +1,417 @@
+// C-ABI of the B200-native SuDoRM-RF forward (see include/sudormrf_b200.h):
+// parameter layout (reference state_dict order), weight packing, workspace
+// planning and the forward orchestration that enqueues every kernel on the
+// caller's stream.
+#include <vector>
+#include <cstring>
+#include "common.cuh"
+
+namespace sdr {
+
+// kernel launchers (levels.cu, pointwise.cu, frontback.cu, tac.cu)
+int launch_depthwise(const float*, const NormIn&, const float*, const float*, float*, double*, int, int, int, int, cudaStream_t);
+int launch_merge(const float* const*, const NormIn*, int, float*, double*, int, int, int, cudaStream_t);
+int launch_pointwise_ffma(const float*, const NormIn&, const float*, const float*, const float*, const float*, int,
+                          float*, double*, int, int, int, int, int, cudaStream_t);
+int launch_encoder(const float*, const float*, float*, double*, int, int, long long, int, int, int, cudaStream_t);
+int launch_overlap_add(const float*, const float*, float*, int, int, int, int, long long, cudaStream_t);
+int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
+int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
+int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------
+// parameter layout: offsets (in floats) of every tensor inside the packed buffer
+// ---------------------------------------------------------------------------
+struct UBlockOff {
+    size_t proj_w, proj_b, proj_g, proj_be, proj_a;
+    size_t dw_w[kMaxDepthApi], dw_b[kMaxDepthApi], dw_g[kMaxDepthApi], dw_be[kMaxDepthApi];
+    size_t fn_g, fn_be, fn_a, res_w, res_b;
+};
+struct TacOff { size_t p[9]; size_t g, be; };
+
+struct Layout {
+    bool ok = false;
+    int A, N, Co, Ci, U, D, K, S, G, hop;
+    int cob, cib;                 // channels seen by one U-ConvBlock (Co/G, Ci/G for groupcomm)
+    bool gc;
+    size_t enc_w, ln_g, ln_be, bn_w, bn_b, mask_a, mask_w, mask_b, dec_w;
+    size_t dec_wt;                // derived: decoder weight as [S*A*K, S*A*N]
+    std::vector<UBlockOff> ub;
+    std::vector<TacOff> tac;
+    std::vector<size_t> off, numel;   // per state_dict entry
+    size_t total = 0;             // floats
+};
+
+static Layout make_layout(const sdr_config* c) {
+    Layout l;
+    if (!c) return l;
+    l.gc = c->variant == 1;
+    if (c->variant != 0 && c->variant != 1) return l;
+    l.A = l.gc ? c->in_audio_channels : 1;
+    l.N = c->enc_num_basis; l.Co = c->out_channels; l.Ci = c->in_channels;
+    l.U = c->num_blocks; l.D = c->upsampling_depth; l.K = c->enc_kernel_size;
+    l.S = c->num_sources; l.G = l.gc ? c->group_size : 1;
+    l.hop = l.K / 2;
+    if (l.A < 1 || l.N < 1 || l.Co < 1 || l.Ci < 1 || l.U < 0 || l.S < 1 || l.G < 1) return l;
+    if (l.D < 1 || l.D > kMaxDepthApi) return l;
+    if (l.K < 3 || (l.K % 2) == 0) return l;          // hop-size arithmetic needs an odd filter (groupcomm_sudormrf_v2.py:255-258)
+    if (l.S * l.A > 16) return l;
+    if (l.gc && (l.Co % l.G || l.Ci % l.G)) return l;
+    l.cob = l.Co / l.G; l.cib = l.Ci / l.G;
+
+    size_t cur = 0;
+    auto add = [&](size_t n) { size_t o = cur; l.off.push_back(o); l.numel.push_back(n); cur += (n + 3) & ~(size_t)3; return o; };
+    l.enc_w = add((size_t)l.N * l.A * l.K);
+    l.ln_g = add(l.N); l.ln_be = add(l.N);
+    l.bn_w = add((size_t)l.Co * l.N); l.bn_b = add(l.Co);
+    for (int i = 0; i < l.U; ++i) {
+        if (l.gc) {
+            TacOff t;
+            const size_t n = l.cob, H = 3 * (size_t)l.cob;
+            t.p[0] = add(H * n); t.p[1] = add(H); t.p[2] = add(1);
+            t.p[3] = add(H * H); t.p[4] = add(H); t.p[5] = add(1);
+            t.p[6] = add(n * 2 * H); t.p[7] = add(n); t.p[8] = add(1);
+            t.g = add(n); t.be = add(n);
+            l.tac.push_back(t);
+        }
+        UBlockOff u;
+        u.proj_w = add((size_t)l.cib * l.cob); u.proj_b = add(l.cib);
+        u.proj_g = add(l.cib); u.proj_be = add(l.cib); u.proj_a = add(1);
+        for (int d = 0; d < l.D; ++d) {
+            u.dw_w[d] = add((size_t)l.cib * 5); u.dw_b[d] = add(l.cib);
+            u.dw_g[d] = add(l.cib); u.dw_be[d] = add(l.cib);
+        }
+        u.fn_g = add(l.cib); u.fn_be = add(l.cib); u.fn_a = add(1);
+        u.res_w = add((size_t)l.cob * l.cib); u.res_b = add(l.cob);
+        l.ub.push_back(u);
+    }
+    l.mask_a = add(1);
+    l.mask_w = add((size_t)l.S * l.N * l.A * l.Co); l.mask_b = add((size_t)l.S * l.N * l.A);
+    l.dec_w = add((size_t)l.N * l.S * l.A * l.S * l.A * l.K);
+    // derived region (not a state_dict entry)
+    l.dec_wt = cur; cur += ((size_t)l.S * l.A * l.K * l.S * l.A * l.N + 3) & ~(size_t)3;
+    l.total = cur;
+    l.ok = true;
+    return l;
+}
+
+static long long padded_len(const Layout& l, long long T) {
+    const long long q = (long long)l.hop << l.D;          // improved_sudormrf.py:244
+    if (T < q) return q;
+    return (T + q - 1) / q * q;
+}
+
+// decoder.weight [C=S*A*N][SA][K]  ->  [SA*K][C]
+__global__ void transpose_decoder_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                         int C, int SAK) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)C * SAK) return;
+    const int c = (int)(i % C), r = (int)(i / C);
+    wt[i] = w[(size_t)c * SAK + r];
+}
+
+// ---------------------------------------------------------------------------
+// workspace plan
+// ---------------------------------------------------------------------------
+struct Plan {
+    long long Tp; int L; int samples;          // samples = B (improved) or B*G
+    int slots; size_t stats_doubles;
+    size_t o_stats, o_e, o_x, o_xt, o_o, o_y, o_z[kMaxDepthApi], o_masked, o_frames, total;  // bytes
+};
+
+static Plan make_plan(const Layout& l, int B, long long T) {
+    Plan p;
+    p.Tp = padded_len(l, T);
+    p.L = (int)(p.Tp / l.hop);
+    p.samples = B * l.G;
+    p.slots = 1 + l.U * (l.D + 2 + (l.gc ? 1 : 0));
+    p.stats_doubles = (size_t)p.slots * p.samples * 2;
+    size_t cur = 0;
+    auto seg = [&](size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t BL = (size_t)B * p.L * sizeof(float);
+    p.o_stats = seg(p.stats_doubles * sizeof(double));
+    p.o_e = seg(BL * l.N);
+    p.o_x = seg(BL * l.Co);
+    p.o_xt = l.gc ? seg(BL * l.Co) : 0;
+    p.o_o = l.gc ? seg(BL * l.Co) : 0;
+    p.o_y = seg(BL * l.Ci);
+    for (int d = 0; d < kMaxDepthApi; ++d) p.o_z[d] = d < l.D ? seg((BL * l.Ci) >> d) : 0;
+    p.o_masked = seg(BL * l.S * l.A * l.N);
+    p.o_frames = seg(BL * l.S * l.A * l.K);
+    p.total = cur;
+    return p;
+}
+
+#define SDR_TRY(expr) do { int _e = (expr); if (_e != SDR_OK) return _e; } while (0)
+
+static int forward_impl(const Layout& l, const float* pk, const float* mixture, float* out,
+                        int B, long long T, int apply_mc, char* ws, cudaStream_t st) {
+    const Plan p = make_plan(l, B, T);
+    const int L = p.L, D = l.D;
+    double* stats = reinterpret_cast<double*>(ws + p.o_stats);
+    float* e = reinterpret_cast<float*>(ws + p.o_e);
+    float* x = reinterpret_cast<float*>(ws + p.o_x);
+    float* xt = l.gc ? reinterpret_cast<float*>(ws + p.o_xt) : nullptr;
+    float* o = l.gc ? reinterpret_cast<float*>(ws + p.o_o) : nullptr;
+    float* y = reinterpret_cast<float*>(ws + p.o_y);
+    float* z[kMaxDepthApi];
+    for (int d = 0; d < D; ++d) z[d] = reinterpret_cast<float*>(ws + p.o_z[d]);
+    float* masked = reinterpret_cast<float*>(ws + p.o_masked);
+    float* frames = reinterpret_cast<float*>(ws + p.o_frames);
+    auto slot = [&](int s) { return stats + (size_t)s * p.samples * 2; };
+    const NormIn none{nullptr, nullptr, nullptr, nullptr, 1.0};
+
+    if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
+
+    // front end: encoder (+stats), ln folded into the bottleneck's operand load
+    SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, st));
+    {
+        NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)l.N * L};
+        SDR_TRY(launch_pointwise_ffma(e, ln, pk + l.bn_w, pk + l.bn_b, nullptr, nullptr, 0,
+                                      x, nullptr, B, l.Co, l.N, L, 0, st));
+    }
+    // separation module
+    const int ns = p.samples, cob = l.cob, cib = l.cib;
+    for (int i = 0; i < l.U; ++i) {
+        const int s0 = 1 + i * (D + 2 + (l.gc ? 1 : 0));
+        const UBlockOff& u = l.ub[i];
+        const float* bin = x;                       // block input == residual
+        if (l.gc) {
+            const TacOff& tc = l.tac[i];
+            const float* tp[9];
+            for (int k = 0; k < 9; ++k) tp[k] = pk + tc.p[k];
+            double* st_tac = slot(s0 + D + 2);
+            SDR_TRY(launch_tac(x, tp, o, st_tac, B, l.G, cob, L, st));
+            NormIn tn{st_tac, pk + tc.g, pk + tc.be, nullptr, (double)cob * L};
+            SDR_TRY(launch_tac_apply(x, o, tn, xt, ns, cob, L, st));
+            bin = xt;
+        }
+        // proj_1x1: raw + stats
+        SDR_TRY(launch_pointwise_ffma(bin, none, pk + u.proj_w, pk + u.proj_b, nullptr, nullptr, 0,
+                                      y, slot(s0), ns, cib, cob, L, 0, st));
+        // level 0: PReLU(GLN(proj)) on load
+        {
+            NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)cib * L};
+            SDR_TRY(launch_depthwise(y, n0, pk + u.dw_w[0], pk + u.dw_b[0], z[0], slot(s0 + 1), ns, cib, L, 1, st));
+        }
+        for (int d = 1; d < D; ++d) {
+            NormIn nd{slot(s0 + d), pk + u.dw_g[d - 1], pk + u.dw_be[d - 1], nullptr, (double)cib * (L >> (d - 1))};
+            SDR_TRY(launch_depthwise(z[d - 1], nd, pk + u.dw_w[d], pk + u.dw_b[d], z[d], slot(s0 + 1 + d),
+                                     ns, cib, L >> (d - 1), 2, st));
+        }
+        // merge
+        {
+            NormIn nm[kMaxDepthApi];
+            const float* zc[kMaxDepthApi];
+            for (int d = 0; d < D; ++d) {
+                nm[d] = NormIn{slot(s0 + 1 + d), pk + u.dw_g[d], pk + u.dw_be[d], nullptr, (double)cib * (L >> d)};
+                zc[d] = z[d];
+            }
+            SDR_TRY(launch_merge(zc, nm, D, y, slot(s0 + D + 1), ns, cib, L, st));   // m reuses y's storage
+        }
+        // res_conv + skip
+        {
+            NormIn nf{slot(s0 + D + 1), pk + u.fn_g, pk + u.fn_be, pk + u.fn_a, (double)cib * L};
+            SDR_TRY(launch_pointwise_ffma(y, nf, pk + u.res_w, pk + u.res_b, bin, nullptr, 0,
+                                          x, nullptr, ns, cob, cib, L, 0, st));
+        }
+    }
+    // mask: PReLU -> 1x1 -> ReLU -> * encoder output
+    {
+        NormIn pm{nullptr, nullptr, nullptr, pk + l.mask_a, 1.0};
+        SDR_TRY(launch_pointwise_ffma(x, pm, pk + l.mask_w, pk + l.mask_b, nullptr, e, l.N,
+                                      masked, nullptr, B, l.S * l.A * l.N, l.Co, L, 1, st));
+    }
+    // decoder: frames = Wd^T masked, then overlap-add / crop / mixture consistency
+    SDR_TRY(launch_pointwise_ffma(masked, none, pk + l.dec_wt, nullptr, nullptr, nullptr, 0,
+                                  frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
+    const float* mix = (apply_mc && l.A == 1) ? mixture : nullptr;
+    SDR_TRY(launch_overlap_add(frames, mix, out, B, l.S * l.A, l.K, L, T, st));
+    return SDR_OK;
+}
+
+}  // namespace sdr
+
+// ===========================================================================
+// extern "C" surface
+// ===========================================================================
+using namespace sdr;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int sdr_abi_version(void) { return SDR_ABI_VERSION; }
+
+const char* sdr_error_string(int code) {
+    switch (code) {
+        case SDR_OK: return "ok";
+        case SDR_ERR_BAD_CONFIG: return "bad model configuration";
+        case SDR_ERR_BAD_ARGUMENT: return "bad argument";
+        case SDR_ERR_WORKSPACE: return "workspace or packed-weight buffer too small";
+        case SDR_ERR_CUDA: return "CUDA call or kernel launch failed";
+        case SDR_ERR_UNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+        default: return "unknown error";
+    }
+}
+
+int sdr_num_params(const sdr_config* cfg) {
+    const Layout l = make_layout(cfg);
+    return l.ok ? (int)l.off.size() : SDR_ERR_BAD_CONFIG;
+}
+
+int64_t sdr_param_numel(const sdr_config* cfg, int index) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok) return SDR_ERR_BAD_CONFIG;
+    if (index < 0 || index >= (int)l.numel.size()) return SDR_ERR_BAD_ARGUMENT;
+    return (int64_t)l.numel[index];
+}
+
+int64_t sdr_padded_length(const sdr_config* cfg, int64_t T) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok) return SDR_ERR_BAD_CONFIG;
+    if (T <= 0) return SDR_ERR_BAD_ARGUMENT;
+    return padded_len(l, T);
+}
+
+size_t sdr_packed_weight_bytes(const sdr_config* cfg) {
+    const Layout l = make_layout(cfg);
+    return l.ok ? l.total * sizeof(float) : 0;
+}
+
+int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_params,
+                     void* packed, size_t packed_bytes, sdr_stream stream) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok) return SDR_ERR_BAD_CONFIG;
+    if (!params || !packed || n_params != (int)l.off.size()) return SDR_ERR_BAD_ARGUMENT;
+    if (packed_bytes < l.total * sizeof(float)) return SDR_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* pk = static_cast<float*>(packed);
+    if (cudaMemsetAsync(pk, 0, l.total * sizeof(float), st) != cudaSuccess) return SDR_ERR_CUDA;
+    for (size_t i = 0; i < l.off.size(); ++i) {
+        if (!params[i]) return SDR_ERR_BAD_ARGUMENT;
+        if (cudaMemcpyAsync(pk + l.off[i], params[i], l.numel[i] * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st) != cudaSuccess) return SDR_ERR_CUDA;
+    }
+    const int C = l.S * l.A * l.N, SAK = l.S * l.A * l.K;
+    const long long n = (long long)C * SAK;
+    transpose_decoder_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pk + l.dec_w, pk + l.dec_wt, C, SAK);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+size_t sdr_workspace_bytes(const sdr_config* cfg, int B, int64_t T) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok || B <= 0 || T <= 0) return 0;
+    return make_plan(l, B, T).total;
+}
+
+static int check_forward_args(const Layout& l, int B, int64_t T) {
+    if (!l.ok) return SDR_ERR_BAD_CONFIG;
+    if (B <= 0 || T <= 0) return SDR_ERR_BAD_ARGUMENT;
+    if (l.gc) {
+        const int n = l.cob;
+        if (!(n == 4 || n == 8 || n == 16 || n == 32) || l.G > 16) return SDR_ERR_UNSUPPORTED;
+    }
+    if (padded_len(l, T) / l.hop > 0x3fffffffLL) return SDR_ERR_UNSUPPORTED;
+    return SDR_OK;
+}
+
+int sdr_forward(const sdr_config* cfg, const void* packed, const float* mixture, float* out,
+                int B, int64_t T, int apply_mixture_consistency,
+                void* workspace, size_t workspace_bytes, sdr_stream stream) {
+    const Layout l = make_layout(cfg);
+    SDR_TRY(check_forward_args(l, B, T));
+    if (!packed || !mixture || !out || !workspace) return SDR_ERR_BAD_ARGUMENT;
+    if (workspace_bytes < make_plan(l, B, T).total) return SDR_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 || reinterpret_cast<uintptr_t>(packed) % 16)
+        return SDR_ERR_BAD_ARGUMENT;
+    return forward_impl(l, static_cast<const float*>(packed), mixture, out, B, T,
+                        apply_mixture_consistency, static_cast<char*>(workspace),
+                        static_cast<cudaStream_t>(stream));
+}
+
+int sdr_forward_launch_count(const sdr_config* cfg) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok) return SDR_ERR_BAD_CONFIG;
+    // encoder + bottleneck + U * (proj + D depthwise + merge + res [+ tac + tac_apply]) + mask + decoder GEMM + overlap-add
+    return 2 + l.U * (l.D + 3 + (l.gc ? 2 : 0)) + 3;
+}
+
+size_t sdr_host_staging_bytes(const sdr_config* cfg, int B, int64_t T) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok || B <= 0 || T <= 0) return 0;
+    const size_t in = ((size_t)B * l.A * T * sizeof(float) + 255) & ~(size_t)255;
+    const size_t outb = ((size_t)B * l.S * l.A * T * sizeof(float) + 255) & ~(size_t)255;
+    return in + outb;
+}
+
+int sdr_forward_host(const sdr_config* cfg, const void* packed, const float* host_mixture,
+                     float* host_out, int B, int64_t T, int apply_mixture_consistency,
+                     void* dev_io, size_t dev_io_bytes, void* workspace, size_t workspace_bytes,
+                     sdr_stream stream) {
+    const Layout l = make_layout(cfg);
+    SDR_TRY(check_forward_args(l, B, T));
+    if (!host_mixture || !host_out || !dev_io) return SDR_ERR_BAD_ARGUMENT;
+    if (dev_io_bytes < sdr_host_staging_bytes(cfg, B, T)) return SDR_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t in_bytes = (size_t)B * l.A * T * sizeof(float);
+    const size_t out_bytes = (size_t)B * l.S * l.A * T * sizeof(float);
+    float* d_in = static_cast<float*>(dev_io);
+    float* d_out = reinterpret_cast<float*>(static_cast<char*>(dev_io) + ((in_bytes + 255) & ~(size_t)255));
+    if (cudaMemcpyAsync(d_in, host_mixture, in_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return SDR_ERR_CUDA;
+    SDR_TRY(sdr_forward(cfg, packed, d_in, d_out, B, T, apply_mixture_consistency, workspace, workspace_bytes, stream));
+    if (cudaMemcpyAsync(host_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return SDR_ERR_CUDA;
+    return SDR_OK;
+}
+
+int sdr_mixture_consistency(const float* est, const float* mix, float* out, int B, int S, int64_t T,
+                            int weights_type, void* scratch, sdr_stream stream) {
+    return launch_mixture_consistency(est, mix, out, B, S, T, weights_type, scratch,
+                                      static_cast<cudaStream_t>(stream));
+}
+
+int sdr_encoder(const float* wav, const float* weight, float* enc, double* stats,
+                int B, int A, int64_t T, int N, int K, int L, sdr_stream stream) {
+    if (!wav || !weight || !enc || !stats) return SDR_ERR_BAD_ARGUMENT;
+    if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
+    return launch_encoder(wav, weight, enc, stats, B, A, T, N, K, L, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const float* bias,
+                  const float* residual, const float* gate, int gate_channels, float* y,
+                  double* stats_out, int samples, int M, int Kc, int L, int epilogue, sdr_stream stream) {
+    if (!x || !W || !y) return SDR_ERR_BAD_ARGUMENT;
+    return launch_pointwise_ffma(x, make_norm(fin), W, bias, residual, gate, gate_channels, y, stats_out,
+                                 samples, M, Kc, L, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_depthwise(const float* x, const sdr_norm_in* fin, const float* w5, const float* bias,
+                  float* y, double* stats_out, int samples, int C, int Lin, int stride, sdr_stream stream) {
+    if (!x || !w5 || !bias || !y || !stats_out) return SDR_ERR_BAD_ARGUMENT;
+    if (stride == 2 && (Lin % 2)) return SDR_ERR_BAD_ARGUMENT;
+    return launch_depthwise(x, make_norm(fin), w5, bias, y, stats_out, samples, C, Lin, stride,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int sdr_merge(const float* const* z, const sdr_norm_in* fins, int depth, float* m, double* stats_out,
+              int samples, int C, int L, sdr_stream stream) {
+    if (!z || !fins || !m || !stats_out || depth < 1 || depth > kMaxDepthApi) return SDR_ERR_BAD_ARGUMENT;
+    NormIn n[kMaxDepthApi];
+    for (int d = 0; d < depth; ++d) n[d] = make_norm(fins + d);
+    return launch_merge(z, n, depth, m, stats_out, samples, C, L, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_tac(const float* x, const float* const* params, float* o, double* stats_out,
+            int B, int G, int n, int L, sdr_stream stream) {
+    if (!x || !params || !o || !stats_out) return SDR_ERR_BAD_ARGUMENT;
+    return launch_tac(x, params, o, stats_out, B, G, n, L, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_overlap_add(const float* frames, const float* mix_or_null, float* out, int B, int SA, int K,
+                    int L, int64_t T, sdr_stream stream) {
+    if (!frames || !out) return SDR_ERR_BAD_ARGUMENT;
+    if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
+    return launch_overlap_add(frames, mix_or_null, out, B, SA, K, L, T, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,226 @@
+// 1x1 Conv1d as a batched GEMM, fp32 FFMA path (exact-parity path; also the
+// path for the small / odd channel counts that cannot fill a tcgen05 tile).
+//
+//   y[s, m, l] = sum_k W[m, k] * f(x[s, k, l]) + bias[m]  (+ residual[s, m, l])
+//   f = deferred GlobLN (+PReLU) of the producer, applied while the activation
+//       tile is staged into shared memory.
+//
+// Replaces (reference file:line)
+//   bottleneck        improved_sudormrf.py:256-259,292   f = GlobLN (ln, :255,291)
+//   proj_1x1.conv     improved_sudormrf.py:174,205       f = identity
+//   res_conv (+skip)  improved_sudormrf.py:196,220       f = GlobLN+PReLU (final_norm :195,218)
+//   mask_net          improved_sudormrf.py:268-269,295-298  f = PReLU, epilogue relu()*encoder
+//   decoder (as GEMM) improved_sudormrf.py:272-279,300   frames = Wd^T . masked
+#include "common.cuh"
+
+namespace sdr {
+
+struct PwArgs {
+    const float* x;
+    NormIn nin;
+    const float* W;
+    const float* bias;
+    const float* residual;
+    const float* gate;
+    int gate_channels;
+    float* y;
+    double* stats_out;
+    int M, K, L;
+    int l_tiles;
+    int epilogue;      // 0 plain, 1 relu(y) * gate
+};
+
+constexpr int kPwThreads = 256;
+constexpr int kBN = 128;
+constexpr int kBK = 16;
+
+template <int BM, bool VEC>
+__global__ void __launch_bounds__(kPwThreads, 2)
+pw_gemm_kernel(const PwArgs a) {
+    constexpr int TM = BM / 16;
+    constexpr int AS = BM + 4;                       // padded row stride of the W tile
+    constexpr int WPT = BM * kBK / kPwThreads;       // W elements per thread per k-tile
+    __shared__ __align__(16) float As[2][kBK][AS];
+    __shared__ __align__(16) float Bs[2][kBK][kBN];
+    __shared__ SampleNorm s_norm;
+    __shared__ float s_red[64];
+
+    const int tid = threadIdx.x;
+    const int sample = blockIdx.x / a.l_tiles;
+    const int l0 = (blockIdx.x - sample * a.l_tiles) * kBN;
+    const int m0 = blockIdx.y * BM;
+    if (tid == 0) s_norm = sample_norm(a.nin, sample);
+    __syncthreads();
+    const SampleNorm sn = s_norm;
+
+    const int tx = tid & 15, ty = tid >> 4;
+    const float* xs = a.x + (size_t)sample * a.K * a.L;
+
+    // staging coordinates
+    const int xk = tid >> 5;            // 0..7 (+8)
+    const int xl = (tid & 31) * 4;      // 0..124
+    const int wk = tid & 15;            // k within tile (lanes along k: coalesced W rows)
+    const int wm = tid >> 4;            // 0..15, + 16*i
+
+    float acc[TM][8];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float wreg[WPT];
+    float4 xreg[2];
+
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+            const int m = m0 + wm + 16 * i, k = k0 + wk;
+            wreg[i] = (m < a.M && k < a.K) ? __ldg(a.W + (size_t)m * a.K + k) : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + xk + 8 * h;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < a.K) {
+                const ChanNorm cn = chan_norm(a.nin, sn, k);
+                const float* p = xs + (size_t)k * a.L + l0 + xl;
+                if (VEC) {
+                    if (l0 + xl < a.L) {
+                        v = ldg4(p);
+                        v.x = apply_norm(cn, v.x); v.y = apply_norm(cn, v.y);
+                        v.z = apply_norm(cn, v.z); v.w = apply_norm(cn, v.w);
+                    }
+                } else {
+                    if (l0 + xl + 0 < a.L) v.x = apply_norm(cn, __ldg(p + 0));
+                    if (l0 + xl + 1 < a.L) v.y = apply_norm(cn, __ldg(p + 1));
+                    if (l0 + xl + 2 < a.L) v.z = apply_norm(cn, __ldg(p + 2));
+                    if (l0 + xl + 3 < a.L) v.w = apply_norm(cn, __ldg(p + 3));
+                }
+            }
+            xreg[h] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) As[buf][wk][wm + 16 * i] = wreg[i];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            *reinterpret_cast<float4*>(&Bs[buf][xk + 8 * h][xl]) = xreg[h];
+    };
+
+    const int nk = (a.K + kBK - 1) / kBK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) load_tiles((kt + 1) * kBK);
+#pragma unroll
+        for (int k = 0; k < kBK; ++k) {
+            float af[TM];
+            if constexpr (BM == 128) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+                af[0] = a0.x; af[1] = a0.y; af[2] = a0.z; af[3] = a0.w;
+                af[4] = a1.x; af[5] = a1.y; af[6] = a1.z; af[7] = a1.w;
+            } else if constexpr (BM == 64) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+                af[0] = a0.x; af[1] = a0.y; af[2] = a0.z; af[3] = a0.w;
+            } else {
+                const float2 a0 = *reinterpret_cast<const float2*>(&As[cur][k][ty * 2]);
+                af[0] = a0.x; af[1] = a0.y;
+            }
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+            const float bf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) store_tiles(cur ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue: bias, residual, gate, store, statistics ----
+    float st_s = 0.f, st_q = 0.f;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int mr;
+        if (BM == 128) mr = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+        else if (BM == 64) mr = ty * 4 + i;
+        else mr = ty * 2 + i;
+        const int m = m0 + mr;
+        if (m >= a.M) continue;
+        const float b = a.bias ? __ldg(a.bias + m) : 0.f;
+        const size_t row = ((size_t)sample * a.M + m) * a.L;
+        const float* grow = (a.epilogue == 1)
+            ? a.gate + ((size_t)sample * a.gate_channels + (m % a.gate_channels)) * a.L : nullptr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = l0 + h * 64 + tx * 4;
+            float o[4] = {acc[i][4 * h + 0] + b, acc[i][4 * h + 1] + b,
+                          acc[i][4 * h + 2] + b, acc[i][4 * h + 3] + b};
+            if (VEC) {
+                if (l < a.L) {
+                    if (a.residual) {
+                        const float4 r = *reinterpret_cast<const float4*>(a.residual + row + l);  // plain load: may alias y (in-place skip)
+                        o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+                    }
+                    if (a.epilogue == 1) {
+                        const float4 g = ldg4(grow + l);
+                        o[0] = fmaxf(o[0], 0.f) * g.x; o[1] = fmaxf(o[1], 0.f) * g.y;
+                        o[2] = fmaxf(o[2], 0.f) * g.z; o[3] = fmaxf(o[3], 0.f) * g.w;
+                    }
+                    *reinterpret_cast<float4*>(a.y + row + l) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { st_s += o[e]; st_q = fmaf(o[e], o[e], st_q); }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (l + e < a.L) {
+                        float v = o[e];
+                        if (a.residual) v += a.residual[row + l + e];
+                        if (a.epilogue == 1) v = fmaxf(v, 0.f) * __ldg(grow + l + e);
+                        a.y[row + l + e] = v;
+                        st_s += v; st_q = fmaf(v, v, st_q);
+                    }
+                }
+            }
+        }
+    }
+    if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
+}
+
+template <int BM>
+static int launch_bm(const PwArgs& a, int samples, bool vec, cudaStream_t st) {
+    const long long gx = (long long)a.l_tiles * samples;
+    const int gy = (a.M + BM - 1) / BM;
+    if (gx > 0x7fffffffLL || gy > 65535) return SDR_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (vec) pw_gemm_kernel<BM, true><<<grid, kPwThreads, 0, st>>>(a);
+    else     pw_gemm_kernel<BM, false><<<grid, kPwThreads, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+int launch_pointwise_ffma(const float* x, const NormIn& nin, const float* W, const float* bias,
+                          const float* residual, const float* gate, int gate_channels,
+                          float* y, double* stats_out, int samples, int M, int K, int L,
+                          int epilogue, cudaStream_t st) {
+    if (samples <= 0 || M <= 0 || K <= 0 || L <= 0) return SDR_ERR_BAD_ARGUMENT;
+    if (epilogue == 1 && (!gate || gate_channels <= 0)) return SDR_ERR_BAD_ARGUMENT;
+    PwArgs a;
+    a.x = x; a.nin = nin; a.W = W; a.bias = bias; a.residual = residual; a.gate = gate;
+    a.gate_channels = gate_channels; a.y = y; a.stats_out = stats_out;
+    a.M = M; a.K = K; a.L = L; a.l_tiles = (L + kBN - 1) / kBN; a.epilogue = epilogue;
+    uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y);
+    if (residual) al |= reinterpret_cast<uintptr_t>(residual);
+    if (gate) al |= reinterpret_cast<uintptr_t>(gate);
+    const bool vec = (L % 4 == 0) && (al % 16 == 0);
+    if (M > 64) return launch_bm<128>(a, samples, vec, st);
+    if (M > 32) return launch_bm<64>(a, samples, vec, st);
+    return launch_bm<32>(a, samples, vec, st);
+}
+
+}  // namespace sdr

@@ -1,0 +1,107 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports
+every symbol include/sudormrf_b200.h declares, and its layout functions agree
+with the reference's state_dict inventory.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import sudo_rm_rf_b200 as P
+from sudo_rm_rf_b200 import _engine, _native
+from oracle import sudormrf_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(REPO, "include", "sudormrf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sdr_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = _native.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert lib.sdr_abi_version() == 1
+    assert lib.sdr_error_string(0) == b"ok"
+    assert b"unknown" not in lib.sdr_error_string(-5)
+
+
+@pytest.mark.parametrize("variant,kw", [
+    ("improved", dict(out_channels=256, in_channels=512, num_blocks=16, upsampling_depth=5,
+                      enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
+    ("improved", dict(out_channels=512, in_channels=512, num_blocks=36, upsampling_depth=6,
+                      enc_kernel_size=21, enc_num_basis=2048, num_sources=2)),
+    ("groupcomm", dict(out_channels=256, in_channels=512, num_blocks=8, upsampling_depth=5,
+                       enc_kernel_size=21, enc_num_basis=512, num_sources=2, group_size=16)),
+    ("groupcomm", dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=3,
+                       enc_kernel_size=11, enc_num_basis=16, num_sources=2, group_size=8,
+                       in_audio_channels=2)),
+])
+def test_layout_matches_state_dict(variant, kw):
+    cls = P.SuDORMRF if variant == "improved" else P.GroupCommSudoRmRf
+    m = cls(**kw)
+    cfg_o = O.Config(variant=variant, **kw)
+    sd = m.state_dict()
+    shapes = O.param_shapes(cfg_o)
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    cfg = _engine.make_config(m)
+    assert _engine.state_dict_names(cfg) == list(sd.keys())
+    lib = _native.lib()
+    assert lib.sdr_num_params(C.byref(cfg)) == len(sd)
+    total = 0
+    for i, v in enumerate(sd.values()):
+        assert lib.sdr_param_numel(C.byref(cfg), i) == v.numel()
+        total += v.numel()
+    assert lib.sdr_packed_weight_bytes(C.byref(cfg)) >= 4 * total
+    for T in (1, 100, 320, 321, 32000, 32079):
+        assert lib.sdr_padded_length(C.byref(cfg), T) == O.padded_length(cfg_o, T)
+    assert lib.sdr_workspace_bytes(C.byref(cfg), 2, 32000) > 0
+
+
+def test_published_parameter_counts():
+    # README.md:122-124 of the reference: 5.02 M / 23.24 M / 0.51 M parameters
+    n = lambda m: sum(p.numel() for p in m.parameters())
+    assert n(P.SuDORMRF(256, 512, 16, 5, 21, 512, 2)) == 5016353
+    assert n(P.GroupCommSudoRmRf(1, 256, 512, 8, 5, 21, 512, 2, 16)) == 507177
+
+
+def test_bad_configs_rejected():
+    lib = _native.lib()
+    bad = _native.SdrConfig(0, 1, 16, 32, 1, 3, 20, 16, 2, 1)      # even kernel
+    assert lib.sdr_num_params(C.byref(bad)) == -1
+    assert lib.sdr_workspace_bytes(C.byref(bad), 1, 100) == 0
+    bad = _native.SdrConfig(1, 1, 30, 64, 1, 3, 21, 16, 2, 4)      # Co % G != 0
+    assert lib.sdr_num_params(C.byref(bad)) == -1
+    with pytest.raises(AssertionError):
+        P.GroupCommSudoRmRf(enc_kernel_size=20)
+
+
+def test_no_cpu_fallback_and_error_conventions():
+    m = P.SuDORMRF(16, 32, 1, 2, 21, 16, 2).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 100))
+    with pytest.raises(RuntimeError, match="3D"):
+        m(torch.zeros(1, 100))
+    with pytest.raises(NotImplementedError):
+        m.sm[0](torch.zeros(1, 16, 10))
+    with pytest.raises(ValueError):
+        P.mixture_consistency.apply(torch.zeros(1, 2, 4), torch.zeros(1, 1, 4), "nope")
+    with pytest.raises(RuntimeError):
+        P.mixture_consistency.apply(torch.zeros(1, 2, 4), torch.zeros(1, 1, 4))
+
+
+def test_state_dict_roundtrip_and_module_prefix():
+    m = P.SuDORMRF(16, 32, 2, 3, 21, 24, 2)
+    cfg = O.Config("improved", 16, 32, 2, 3, 21, 24, 2)
+    sd = O.make_state_dict(cfg, seed=1)
+    m.load_state_dict(sd)
+    # DataParallel-saved checkpoints carry a "module." prefix (run_improved_sudormrf.py:221-227)
+    dp = {"module." + k: v for k, v in sd.items()}
+    m.load_state_dict({k[len("module."):]: v for k, v in dp.items()})
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])

@@ -1,0 +1,197 @@
+"""Whole-model parity on the GPU, through the reference-facing nn.Module API
+(which calls the C-ABI): golden fixtures of the reference, the oracle at the
+BASELINE.json shapes, and size-independent properties at full size.
+
+Tolerance (north_star / SURVEY §8d): max|y-ref| <= 1e-3 * max|ref| per sample
+and rel-L2 <= 1e-3 against the reference's fp32 forward."""
+import pytest
+import torch
+
+import sudo_rm_rf_b200 as P
+from oracle import sudormrf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-3
+
+
+def build(variant, kw, sd):
+    cls = P.SuDORMRF if variant == "improved" else P.GroupCommSudoRmRf
+    m = cls(**kw)
+    m.load_state_dict(sd)
+    return m.to(DEV).eval()
+
+
+def test_native_library_is_loaded():
+    """The product path must be the CUDA extension (no eager fallback)."""
+    from sudo_rm_rf_b200 import _native
+    _native.lib()
+    maps = open("/proc/self/maps").read()
+    assert "libsudormrf_b200.so" in maps
+
+
+def test_golden_fixtures(golden):
+    meta, sd, x, outs, taps = golden
+    m = build(meta["variant"], meta["kwargs"], sd)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert y.shape == outs["output"].shape and y.dtype == torch.float32 and y.is_cuda
+    e = O.parity_errors(y, outs["output"])
+    assert max(e) < TOL, e
+    assert max(e) < 1e-4, e          # the fp32 path should be far inside the budget
+    if "mc_uniform" in outs:
+        with torch.no_grad():
+            ymc = m.separate(x.to(DEV), mixture_consistency=True)
+        assert max(O.parity_errors(ymc, outs["mc_uniform"])) < TOL
+        got = P.mixture_consistency.apply(y, x.to(DEV))
+        assert max(O.parity_errors(got, outs["mc_uniform"])) < TOL
+        got = P.mixture_consistency.apply(y, x.to(DEV), "magsq")
+        assert max(O.parity_errors(got, outs["mc_magsq"])) < TOL
+
+
+FULL = [
+    # BASELINE.json configs, batch reduced so the CPU oracle finishes in seconds
+    ("cfg1_improved_u8_512", "improved",
+     dict(out_channels=256, in_channels=512, num_blocks=8, upsampling_depth=5,
+          enc_kernel_size=21, enc_num_basis=512, num_sources=2), 1, 32000),
+    ("cfg2_improved_u16_512", "improved",
+     dict(out_channels=256, in_channels=512, num_blocks=16, upsampling_depth=5,
+          enc_kernel_size=21, enc_num_basis=512, num_sources=2), 2, 32079),
+    ("cfg4_groupcomm_u8_512", "groupcomm",
+     dict(out_channels=256, in_channels=512, num_blocks=8, upsampling_depth=5,
+          enc_kernel_size=21, enc_num_basis=512, num_sources=2, group_size=16), 2, 32000),
+    ("cfg3_improved_u36_2048_short", "improved",
+     dict(out_channels=512, in_channels=512, num_blocks=36, upsampling_depth=6,
+          enc_kernel_size=21, enc_num_basis=2048, num_sources=2), 1, 8000),
+]
+
+
+@pytest.mark.parametrize("name,variant,kw,B,T", FULL, ids=[f[0] for f in FULL])
+@pytest.mark.parametrize("weights", ["perturbed", "default"])
+def test_full_size_vs_oracle(name, variant, kw, B, T, weights):
+    if weights == "default" and not name.startswith("cfg2"):
+        pytest.skip("default-init weights checked on cfg2 only")
+    cfg = O.Config(variant=variant, **kw)
+    sd = O.make_state_dict(cfg, seed=21, perturbed=(weights == "perturbed"))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 1, T, generator=g)
+    x = (x - x.mean(-1, keepdim=True)) / (x.std(-1, keepdim=True) + 1e-9)   # README.md:101-103
+    ref = O.forward(cfg, sd, x)
+    m = build(variant, kw, sd)
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert y.shape == ref.shape
+    e = O.parity_errors(y, ref)
+    print(name, weights, "rel_max %.3e rel_l2 %.3e" % e)
+    assert max(e) < TOL, e
+
+
+def test_properties_at_benchmark_size():
+    """Size-independent checks at the cfg-2 benchmark shape (B=32 x 4 s @ 8 kHz)."""
+    kw = dict(out_channels=256, in_channels=512, num_blocks=16, upsampling_depth=5,
+              enc_kernel_size=21, enc_num_basis=512, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=5)
+    m = build("improved", kw, sd)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(32, 1, 32000, generator=g).to(DEV)      # the reference's bench input
+    with torch.no_grad():
+        y = m(x)
+        assert y.shape == (32, 2, 32000) and torch.isfinite(y).all()
+        # (1) samples are independent: a sample run alone gives the same estimate
+        y1 = m(x[5:6])
+        assert max(O.parity_errors(y1, y[5:6])) < 1e-5
+        # (2) batch-permutation equivariance
+        perm = torch.randperm(32, generator=g).to(DEV)
+        yp = m(x[perm])
+        assert max(O.parity_errors(yp, y[perm])) < 1e-5
+        # (3) mixture consistency: corrected estimates sum to the mixture
+        ymc = m.separate(x, mixture_consistency=True)
+        assert torch.allclose(ymc.sum(1, keepdim=True), x, atol=1e-4)
+        assert max(O.parity_errors(ymc, P.mixture_consistency.apply(y, x))) < 1e-6
+        # (4) implicit padding == explicit zero padding (improved_sudormrf.py:303-314)
+        xo = x[:2, :, :31999]
+        yo = m(xo)
+        xz = torch.zeros(2, 1, 32320, device=DEV)
+        xz[..., :31999] = xo
+        yz = m(xz)
+        assert yo.shape[-1] == 31999
+        assert max(O.parity_errors(yo, yz[..., :31999])) < 1e-5
+        # (5) spot check one sample of the big batch against the oracle
+        ref = O.forward(cfg, sd, x[7:8].cpu())
+        assert max(O.parity_errors(y[7:8], ref)) < TOL
+
+
+def test_host_entry_and_dtype_handling():
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+              enc_kernel_size=21, enc_num_basis=48, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=3)
+    m = build("improved", kw, sd)
+    x = torch.randn(3, 1, 4001, generator=torch.Generator().manual_seed(0))
+    ref = O.forward(cfg, sd, x)
+    hx = x.pin_memory()
+    hy = m.forward_host(hx)
+    torch.cuda.synchronize()
+    assert max(O.parity_errors(hy, ref)) < 1e-4
+    with torch.no_grad():
+        y64 = m(x.double().to(DEV))          # any float dtype is cast to fp32 (reference :312)
+        y16 = m(x.half().to(DEV))
+    assert y64.dtype == torch.float32
+    assert max(O.parity_errors(y64, ref)) < 1e-4
+    assert max(O.parity_errors(y16, O.forward(cfg, sd, x.half().float()))) < 1e-4
+    # weights updated in place are re-packed
+    with torch.no_grad():
+        m.bottleneck.bias.add_(0.5)
+        y2 = m(x.to(DEV))
+    sd2 = dict(sd)
+    sd2["bottleneck.bias"] = sd["bottleneck.bias"] + 0.5
+    assert max(O.parity_errors(y2, O.forward(cfg, sd2, x))) < 1e-4
+
+
+def test_training_mode_with_grad_raises_and_eval_runs():
+    m = P.SuDORMRF(16, 32, 1, 2, 21, 16, 2).to(DEV)
+    x = torch.randn(1, 1, 400, device=DEV)
+    m.train()
+    with pytest.raises(RuntimeError, match="inference"):
+        m(x)
+    m.eval()
+    y = m(x)                                  # simple_whamr_evaluation.py:145 calls without no_grad
+    assert not y.requires_grad
+
+
+def test_cuda_graph_capture_replays():
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+              enc_kernel_size=21, enc_num_basis=48, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    m = build("improved", kw, O.make_state_dict(cfg, seed=3))
+    x = torch.randn(2, 1, 4000, device=DEV)
+    with torch.no_grad():
+        want = m(x).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = m(x)
+        x.copy_(torch.randn_like(x))
+        g.replay()
+        want2 = m(x)
+    torch.cuda.synchronize()
+    assert max(O.parity_errors(y, want2)) < 1e-6
+    assert max(O.parity_errors(want, want2)) > 1e-3
+
+
+def test_data_parallel_wrapper_single_device():
+    """nn.DataParallel(model) keeps working (run_improved_sudormrf.py:118)."""
+    kw = dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=3,
+              enc_kernel_size=21, enc_num_basis=32, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=4)
+    m = torch.nn.DataParallel(build("improved", kw, sd)).cuda().eval()
+    x = torch.randn(4, 1, 1000, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        y = m(x.cuda())
+    assert max(O.parity_errors(y, O.forward(cfg, sd, x))) < 1e-4

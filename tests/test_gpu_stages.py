@@ -1,0 +1,245 @@
+"""Stage-level parity on the GPU: every per-stage C-ABI entry point against the
+same torch ops the oracle uses (fp32).  Tolerances are fp32-reassociation
+sized (these kernels are exact fp32 FFMA paths)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from sudo_rm_rf_b200 import _native as N
+from oracle import sudormrf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def p(t):
+    return C.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def norm_in(stats=None, gamma=None, beta=None, prelu=None, count=1.0):
+    return N.SdrNormIn(stats.data_ptr() if stats is not None else 0,
+                       gamma.data_ptr() if gamma is not None else 0,
+                       beta.data_ptr() if beta is not None else 0,
+                       prelu.data_ptr() if prelu is not None else 0, float(count))
+
+
+def raw_stats(x):
+    """(sum, sumsq) per sample, fp64, as the producers accumulate them."""
+    xd = x.double().reshape(x.shape[0], -1)
+    return torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=1).contiguous()
+
+
+def check_stats(got, x, rtol=1e-5):
+    want = raw_stats(x)
+    scale = want.abs().amax(0, keepdim=True) + 1e-12
+    assert ((got - want).abs() / scale).max() < rtol, (got, want)
+
+
+def close(a, b, tol=2e-5):
+    e = O.parity_errors(a, b)
+    assert max(e) < tol, e
+
+
+def ref_norm(x, gamma, beta, prelu=None):
+    y = O.glob_ln(x, gamma, beta)
+    return O.prelu1(y, prelu) if prelu is not None else y
+
+
+@pytest.mark.parametrize("samples,C_,L,stride,prelu", [
+    (3, 32, 3200, 1, True), (2, 32, 3200, 2, False), (2, 16, 200, 2, False),
+    (2, 24, 104, 1, True), (5, 7, 26, 1, False), (5, 7, 26, 2, False), (1, 3, 2, 2, False),
+    (2, 512, 800, 2, False), (4, 5, 4, 1, True),
+])
+def test_depthwise(samples, C_, L, stride, prelu):
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(samples, C_, L, generator=g) * 2 + 0.7).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C_, generator=g)).to(DEV)
+    slope = torch.tensor([0.3], device=DEV) if prelu else None
+    w = torch.randn(C_, 1, 5, generator=g).to(DEV)
+    b = torch.randn(C_, generator=g).to(DEV)
+    stats_in = raw_stats(x).to(DEV)
+    Lout = (L - 1) // stride + 1
+    y = torch.full((samples, C_, Lout), float("nan"), device=DEV)
+    stats_out = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    nin = norm_in(stats_in, gamma, beta, slope, C_ * L)
+    N.check(N.lib().sdr_depthwise(p(x), C.byref(nin), p(w), p(b), p(y), p(stats_out),
+                                  samples, C_, L, stride, stream()))
+    want = F.conv1d(ref_norm(x, gamma, beta, slope), w, b, stride=stride, padding=2, groups=C_)
+    close(y, want)
+    check_stats(stats_out, want)
+
+
+@pytest.mark.parametrize("samples,C_,L,depth", [
+    (2, 32, 3200, 5), (3, 16, 64, 6), (2, 8, 32, 1), (2, 5, 2, 1), (2, 6, 6, 2), (1, 512, 3200, 5),
+])
+def test_merge(samples, C_, L, depth):
+    g = torch.Generator().manual_seed(1)
+    zs, gammas, betas, stats = [], [], [], []
+    for d in range(depth):
+        z = (torch.randn(samples, C_, L >> d, generator=g) + 0.3 * d).to(DEV)
+        zs.append(z)
+        gammas.append((1 + 0.3 * torch.randn(C_, generator=g)).to(DEV))
+        betas.append((0.2 * torch.randn(C_, generator=g)).to(DEV))
+        stats.append(raw_stats(z).to(DEV))
+    fins = (N.SdrNormIn * depth)(*[norm_in(stats[d], gammas[d], betas[d], None, C_ * (L >> d))
+                                  for d in range(depth)])
+    zp = (C.c_void_p * depth)(*[z.data_ptr() for z in zs])
+    m = torch.full((samples, C_, L), float("nan"), device=DEV)
+    st = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    N.check(N.lib().sdr_merge(zp, fins, depth, p(m), p(st), samples, C_, L, stream()))
+    levels = [ref_norm(zs[d], gammas[d], betas[d]) for d in range(depth)]
+    for _ in range(depth - 1):
+        top = levels.pop()
+        levels[-1] = levels[-1] + F.interpolate(top, scale_factor=2, mode="nearest")
+    close(m, levels[0])
+    check_stats(st, levels[0])
+
+
+@pytest.mark.parametrize("samples,M,K,L,mode", [
+    (2, 256, 512, 3200, "norm"),          # bottleneck-like
+    (2, 512, 256, 640, "plain_stats"),    # proj_1x1
+    (2, 256, 512, 640, "res"),            # res_conv + skip (in place)
+    (2, 1024, 256, 384, "mask"),          # mask_net + relu * encoder
+    (3, 42, 1024, 200, "plain"),          # decoder GEMM (BM=64 tile)
+    (4, 32, 16, 3200, "plain_stats"),     # groupcomm proj (BM=32 tile)
+    (4, 16, 32, 96, "res"),               # groupcomm res
+    (2, 48, 20, 26, "norm"),              # odd sizes, scalar path (L % 4 != 0)
+    (2, 130, 33, 100, "res"),             # M, K not multiples of the tile
+    (1, 7, 5, 2, "mask"),
+])
+def test_pointwise(samples, M, K, L, mode):
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(samples, K, L, generator=g) + 0.5).to(DEV)
+    W = (torch.randn(M, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(M, generator=g).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(K, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(K, generator=g)).to(DEV)
+    slope = torch.tensor([0.2], device=DEV)
+    stats_in = raw_stats(x).to(DEV)
+    y = torch.full((samples, M, L), float("nan"), device=DEV)
+    st = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    residual = gate = None
+    gate_ch = 0
+    epi = 0
+    if mode == "norm":
+        nin = norm_in(stats_in, gamma, beta, None, K * L)
+        fx = ref_norm(x, gamma, beta)
+    elif mode == "res":
+        nin = norm_in(stats_in, gamma, beta, slope, K * L)
+        fx = ref_norm(x, gamma, beta, slope)
+        residual = torch.randn(samples, M, L, generator=g).to(DEV)
+        y = residual.clone()                  # in-place skip connection
+    elif mode == "mask":
+        nin = norm_in(None, None, None, slope, 1.0)
+        fx = O.prelu1(x, slope)
+        gate_ch = max(1, M // 2) if M % 2 == 0 else M
+        gate = torch.randn(samples, gate_ch, L, generator=g).to(DEV)
+        epi = 1
+    else:
+        nin = norm_in()
+        fx = x
+    want = torch.einsum("mk,skl->sml", W.double(), fx.double()) + bias.double().view(1, -1, 1)
+    if mode == "res":
+        want = want + residual.double()
+        res_ptr = p(y)
+    else:
+        res_ptr = p(None)
+    if mode == "mask":
+        idx = torch.arange(M, device=DEV) % gate_ch
+        want = torch.relu(want) * gate.double()[:, idx, :]
+    want_stats = mode in ("plain_stats",)
+    N.check(N.lib().sdr_pointwise(p(x), C.byref(nin), p(W), p(bias), res_ptr, p(gate), gate_ch,
+                                  p(y), p(st) if want_stats else p(None),
+                                  samples, M, K, L, epi, stream()))
+    close(y, want.float(), tol=3e-5)
+    if want_stats:
+        check_stats(st, want.float(), rtol=3e-5)
+
+
+@pytest.mark.parametrize("B,A,T,N_,K,D", [
+    (2, 1, 32000, 512, 21, 5), (3, 1, 517, 24, 21, 3), (2, 1, 100, 32, 21, 5),
+    (2, 2, 333, 16, 11, 3), (1, 1, 7, 70, 21, 1), (1, 1, 3000, 64, 91, 4),
+])
+def test_encoder(B, A, T, N_, K, D):
+    g = torch.Generator().manual_seed(3)
+    cfg = O.Config(enc_kernel_size=K, upsampling_depth=D)
+    Tp = O.padded_length(cfg, T)
+    hop = K // 2
+    L = Tp // hop
+    wav = torch.randn(B, A, T, generator=g).to(DEV)
+    w = torch.randn(N_, A, K, generator=g).to(DEV)
+    enc = torch.full((B, N_, L), float("nan"), device=DEV)
+    st = torch.zeros(B, 2, dtype=torch.float64, device=DEV)
+    N.check(N.lib().sdr_encoder(p(wav), p(w), p(enc), p(st), B, A, T, N_, K, L, stream()))
+    xp = torch.zeros(B, A, Tp, device=DEV)
+    xp[..., :T] = wav
+    want = F.conv1d(xp, w, None, stride=hop, padding=hop)
+    assert want.shape[-1] == L
+    close(enc, want)
+    check_stats(st, want)
+
+
+@pytest.mark.parametrize("B,SA,K,L,T,mc", [
+    (2, 2, 21, 3200, 32000, False), (2, 2, 21, 3232, 32079, True), (3, 3, 21, 64, 640, False),
+    (2, 4, 11, 72, 333, False), (1, 2, 21, 32, 7, True), (1, 2, 91, 80, 3000, False),
+])
+def test_overlap_add(B, SA, K, L, T, mc):
+    g = torch.Generator().manual_seed(4)
+    hop = K // 2
+    C_ = 6
+    masked = torch.randn(B, C_, L, generator=g).to(DEV)
+    wd = torch.randn(C_, SA, K, generator=g).to(DEV)
+    # frames[b, sa*K+j, t] = sum_c wd[c,sa,j] * masked[b,c,t]
+    frames = torch.einsum("csj,bct->bsjt", wd, masked).reshape(B, SA * K, L).contiguous()
+    mix = torch.randn(B, 1, T, generator=g).to(DEV) if mc else None
+    out = torch.full((B, SA, T), float("nan"), device=DEV)
+    N.check(N.lib().sdr_overlap_add(p(frames), p(mix), p(out), B, SA, K, L, T, stream()))
+    want = F.conv_transpose1d(masked, wd, None, stride=hop, padding=hop,
+                              output_padding=hop - 1)[..., :T]
+    if mc:
+        want = O.mixture_consistency(want.cpu(), mix.cpu()).to(DEV)
+    close(out, want)
+
+
+@pytest.mark.parametrize("B,G,n,L", [(2, 16, 16, 3200), (2, 4, 8, 100), (3, 8, 4, 33),
+                                     (1, 2, 32, 40), (2, 16, 16, 31)])
+def test_tac(B, G, n, L):
+    g = torch.Generator().manual_seed(5)
+    H = 3 * n
+    cfg = O.Config(variant="groupcomm", out_channels=G * n, in_channels=2 * G * n, num_blocks=1,
+                   upsampling_depth=1, group_size=G)
+    sd = {k[len("sm.0.TAC."):]: v.to(DEV) for k, v in O.make_state_dict(cfg, seed=9).items()
+          if k.startswith("sm.0.TAC.")}
+    x = torch.randn(B, G, n, L, generator=g).to(DEV)
+    names = ["TAC_input.0.weight", "TAC_input.0.bias", "TAC_input.1.weight",
+             "TAC_mean.0.weight", "TAC_mean.0.bias", "TAC_mean.1.weight",
+             "TAC_output.0.weight", "TAC_output.0.bias", "TAC_output.1.weight"]
+    assert sd["TAC_mean.0.weight"].shape == (H, H)
+    params = (C.c_void_p * 9)(*[sd[k].contiguous().data_ptr() for k in names])
+    o = torch.full((B, G, n, L), float("nan"), device=DEV)
+    st = torch.zeros(B * G, 2, dtype=torch.float64, device=DEV)
+    N.check(N.lib().sdr_tac(p(x), params, p(o), p(st), B, G, n, L, stream()))
+    taps = {}
+    O.tac(x, sd, "", taps)
+    want = taps["TAC_output"]
+    close(o, want)
+    check_stats(st, want.reshape(B * G, n, L))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "magsq"])
+def test_mixture_consistency(kind):
+    import sudo_rm_rf_b200.mixture_consistency as mc
+    g = torch.Generator().manual_seed(6)
+    est = torch.randn(3, 2, 32079, generator=g)
+    mix = torch.randn(3, 1, 32079, generator=g)
+    got = mc.apply(est.to(DEV), mix.to(DEV), kind)
+    close(got, O.mixture_consistency(est, mix, kind), tol=1e-5)
+    if kind == "uniform":
+        assert torch.allclose(got.sum(1, keepdim=True).cpu(), mix, atol=1e-5)
