@@ -145,6 +145,17 @@ int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const 
                   float* y, double* stats_out,
                   int samples, int M, int Kc, int L, int epilogue, sdr_stream stream);
 
+/* Tensor-core (tcgen05, bf16x3 split, fp32 accumulate) variant of sdr_pointwise for
+ * channel counts that fill a tile: M % 128 == 0 and Kc % 64 == 0.  The weight is
+ * first converted to pre-swizzled bf16 hi/lo shared-memory images (bulk-TMA source);
+ * sdr_pointwise_mma_packed_bytes returns 0 when the shape is not eligible.           */
+size_t sdr_pointwise_mma_packed_bytes(int M, int Kc);
+int sdr_pointwise_mma_pack(const float* W, int M, int Kc, void* packed, sdr_stream stream);
+int sdr_pointwise_mma(const float* x, const sdr_norm_in* fin, const void* packed_w, const float* bias,
+                      const float* residual, const float* gate, int gate_channels,
+                      float* y, double* stats_out,
+                      int samples, int M, int Kc, int L, int epilogue, sdr_stream stream);
+
 /* depthwise Conv1d(k=5, padding=2, stride 1|2, groups=C) on the deferred-normalised
  * input (improved_sudormrf.py:178-189,206-211).  x [samples,C,Lin] ->
  * y [samples,C,Lout] raw + stats.                                            */

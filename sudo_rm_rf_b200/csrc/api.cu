@@ -6,6 +6,8 @@
 #include <cstring>
 #include "common.cuh"
 
+#define SDR_TRY(expr) do { int _e = (expr); if (_e != SDR_OK) return _e; } while (0)
+
 namespace sdr {
 
 // kernel launchers (levels.cu, pointwise.cu, frontback.cu, tac.cu)
@@ -18,6 +20,22 @@ int launch_overlap_add(const float*, const float*, float*, int, int, int, int, l
 int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
+// tensor-core path (pointwise_mma.cu)
+bool pointwise_mma_eligible(int M, int K);
+size_t pointwise_mma_packed_bytes(int M, int K);
+int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t);
+int launch_pointwise_mma(const float*, const NormIn&, const void*, const float*, const float*, const float*, int,
+                         float*, double*, int, int, int, int, int, cudaStream_t);
+
+// One 1x1 convolution: tensor cores when the channel counts fill a tcgen05 tile, FFMA otherwise.
+static int pointwise(const float* x, const NormIn& nin, const float* W, const float* wpk, const float* bias,
+                     const float* residual, const float* gate, int gate_channels, float* y, double* stats,
+                     int samples, int M, int K, int L, int epilogue, cudaStream_t st) {
+    if (wpk) return launch_pointwise_mma(x, nin, wpk, bias, residual, gate, gate_channels, y, stats,
+                                         samples, M, K, L, epilogue, st);
+    return launch_pointwise_ffma(x, nin, W, bias, residual, gate, gate_channels, y, stats,
+                                 samples, M, K, L, epilogue, st);
+}
 
 // ---------------------------------------------------------------------------
 // parameter layout: offsets (in floats) of every tensor inside the packed buffer
@@ -26,6 +44,7 @@ struct UBlockOff {
     size_t proj_w, proj_b, proj_g, proj_be, proj_a;
     size_t dw_w[kMaxDepthApi], dw_b[kMaxDepthApi], dw_g[kMaxDepthApi], dw_be[kMaxDepthApi];
     size_t fn_g, fn_be, fn_a, res_w, res_b;
+    size_t proj_pk, res_pk;       // tensor-core images (0 = not eligible -> FFMA kernel)
 };
 struct TacOff { size_t p[9]; size_t g, be; };
 
@@ -36,6 +55,7 @@ struct Layout {
     bool gc;
     size_t enc_w, ln_g, ln_be, bn_w, bn_b, mask_a, mask_w, mask_b, dec_w;
     size_t dec_wt;                // derived: decoder weight as [S*A*K, S*A*N]
+    size_t bn_pk, mask_pk;        // derived: tensor-core weight images (0 = not eligible)
     std::vector<UBlockOff> ub;
     std::vector<TacOff> tac;
     std::vector<size_t> off, numel;   // per state_dict entry
@@ -90,6 +110,18 @@ static Layout make_layout(const sdr_config* c) {
     l.dec_w = add((size_t)l.N * l.S * l.A * l.S * l.A * l.K);
     // derived region (not a state_dict entry)
     l.dec_wt = cur; cur += ((size_t)l.S * l.A * l.K * l.S * l.A * l.N + 3) & ~(size_t)3;
+    cur = (cur + 63) & ~(size_t)63;                       // 256 B alignment for the bulk-TMA images
+    auto add_pk = [&](int M, int K) -> size_t {
+        const size_t b = pointwise_mma_packed_bytes(M, K);
+        if (!b) return 0;
+        const size_t o = cur; cur += b / sizeof(float); return o;
+    };
+    l.bn_pk = add_pk(l.Co, l.N);
+    for (int i = 0; i < l.U; ++i) {
+        l.ub[i].proj_pk = add_pk(l.cib, l.cob);
+        l.ub[i].res_pk = add_pk(l.cob, l.cib);
+    }
+    l.mask_pk = add_pk(l.S * l.A * l.N, l.Co);
     l.total = cur;
     l.ok = true;
     return l;
@@ -142,7 +174,6 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     return p;
 }
 
-#define SDR_TRY(expr) do { int _e = (expr); if (_e != SDR_OK) return _e; } while (0)
 
 static int forward_impl(const Layout& l, const float* pk, const float* mixture, float* out,
                         int B, long long T, int apply_mc, char* ws, cudaStream_t st) {
@@ -167,8 +198,8 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, st));
     {
         NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)l.N * L};
-        SDR_TRY(launch_pointwise_ffma(e, ln, pk + l.bn_w, pk + l.bn_b, nullptr, nullptr, 0,
-                                      x, nullptr, B, l.Co, l.N, L, 0, st));
+        SDR_TRY(pointwise(e, ln, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
+                          x, nullptr, B, l.Co, l.N, L, 0, st));
     }
     // separation module
     const int ns = p.samples, cob = l.cob, cib = l.cib;
@@ -187,8 +218,8 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
             bin = xt;
         }
         // proj_1x1: raw + stats
-        SDR_TRY(launch_pointwise_ffma(bin, none, pk + u.proj_w, pk + u.proj_b, nullptr, nullptr, 0,
-                                      y, slot(s0), ns, cib, cob, L, 0, st));
+        SDR_TRY(pointwise(bin, none, pk + u.proj_w, u.proj_pk ? pk + u.proj_pk : nullptr, pk + u.proj_b,
+                          nullptr, nullptr, 0, y, slot(s0), ns, cib, cob, L, 0, st));
         // level 0: PReLU(GLN(proj)) on load
         {
             NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)cib * L};
@@ -212,15 +243,15 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
         // res_conv + skip
         {
             NormIn nf{slot(s0 + D + 1), pk + u.fn_g, pk + u.fn_be, pk + u.fn_a, (double)cib * L};
-            SDR_TRY(launch_pointwise_ffma(y, nf, pk + u.res_w, pk + u.res_b, bin, nullptr, 0,
-                                          x, nullptr, ns, cob, cib, L, 0, st));
+            SDR_TRY(pointwise(y, nf, pk + u.res_w, u.res_pk ? pk + u.res_pk : nullptr, pk + u.res_b, bin,
+                              nullptr, 0, x, nullptr, ns, cob, cib, L, 0, st));
         }
     }
     // mask: PReLU -> 1x1 -> ReLU -> * encoder output
     {
         NormIn pm{nullptr, nullptr, nullptr, pk + l.mask_a, 1.0};
-        SDR_TRY(launch_pointwise_ffma(x, pm, pk + l.mask_w, pk + l.mask_b, nullptr, e, l.N,
-                                      masked, nullptr, B, l.S * l.A * l.N, l.Co, L, 1, st));
+        SDR_TRY(pointwise(x, pm, pk + l.mask_w, l.mask_pk ? pk + l.mask_pk : nullptr, pk + l.mask_b, nullptr,
+                          e, l.N, masked, nullptr, B, l.S * l.A * l.N, l.Co, L, 1, st));
     }
     // decoder: frames = Wd^T masked, then overlap-add / crop / mixture consistency
     SDR_TRY(launch_pointwise_ffma(masked, none, pk + l.dec_wt, nullptr, nullptr, nullptr, 0,
@@ -295,7 +326,15 @@ int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_pa
     const int C = l.S * l.A * l.N, SAK = l.S * l.A * l.K;
     const long long n = (long long)C * SAK;
     transpose_decoder_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pk + l.dec_w, pk + l.dec_wt, C, SAK);
-    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+    if (cudaGetLastError() != cudaSuccess) return SDR_ERR_CUDA;
+    // bf16 hi/lo, pre-swizzled tensor-core images of every eligible 1x1 weight
+    if (l.bn_pk) SDR_TRY(pack_pointwise_mma(pk + l.bn_w, l.Co, l.N, pk + l.bn_pk, st));
+    for (int i = 0; i < l.U; ++i) {
+        if (l.ub[i].proj_pk) SDR_TRY(pack_pointwise_mma(pk + l.ub[i].proj_w, l.cib, l.cob, pk + l.ub[i].proj_pk, st));
+        if (l.ub[i].res_pk) SDR_TRY(pack_pointwise_mma(pk + l.ub[i].res_w, l.cob, l.cib, pk + l.ub[i].res_pk, st));
+    }
+    if (l.mask_pk) SDR_TRY(pack_pointwise_mma(pk + l.mask_w, l.S * l.A * l.N, l.Co, pk + l.mask_pk, st));
+    return SDR_OK;
 }
 
 size_t sdr_workspace_bytes(const sdr_config* cfg, int B, int64_t T) {
@@ -382,6 +421,20 @@ int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const 
     if (!x || !W || !y) return SDR_ERR_BAD_ARGUMENT;
     return launch_pointwise_ffma(x, make_norm(fin), W, bias, residual, gate, gate_channels, y, stats_out,
                                  samples, M, Kc, L, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+size_t sdr_pointwise_mma_packed_bytes(int M, int Kc) { return pointwise_mma_packed_bytes(M, Kc); }
+
+int sdr_pointwise_mma_pack(const float* W, int M, int Kc, void* packed, sdr_stream stream) {
+    if (!W || !packed) return SDR_ERR_BAD_ARGUMENT;
+    return pack_pointwise_mma(W, M, Kc, packed, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_pointwise_mma(const float* x, const sdr_norm_in* fin, const void* packed_w, const float* bias,
+                      const float* residual, const float* gate, int gate_channels, float* y,
+                      double* stats_out, int samples, int M, int Kc, int L, int epilogue, sdr_stream stream) {
+    return launch_pointwise_mma(x, make_norm(fin), packed_w, bias, residual, gate, gate_channels, y, stats_out,
+                                samples, M, Kc, L, epilogue, static_cast<cudaStream_t>(stream));
 }
 
 int sdr_depthwise(const float* x, const sdr_norm_in* fin, const float* w5, const float* bias,

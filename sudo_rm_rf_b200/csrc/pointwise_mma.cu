@@ -1,0 +1,477 @@
+// 1x1 Conv1d on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   y[s, m, l] = sum_k W[m, k] * f(x[s, k, l]) + bias[m]   (+ residual | relu()*gate)
+//
+// GEMM view per tile: D[128 positions, N channels] = A[128, K] * B[N, K]^T with
+//   A = f(x) tile, produced on the fly: the activation tile cannot be TMA'd
+//       straight into the MMA because the producer's deferred GlobLN(+PReLU)
+//       has to be applied first.  8 transform warps read x with coalesced
+//       128 B row segments, apply the per-channel affine (+PReLU), split the
+//       fp32 value into bf16 hi + bf16 lo, and store both into the K-major
+//       SWIZZLE_128B shared-memory layout the UMMA descriptors expect.
+//   B = weights, pre-split into bf16 hi/lo and pre-swizzled at pack time, so a
+//       k-block is ONE cp.async.bulk (TMA bulk copy) of a contiguous image.
+//   D = fp32 accumulator in TMEM, 2 stages x 256 columns, so the epilogue of
+//       tile i overlaps the main loop of tile i+1 (persistent CTAs, 1 per SM).
+// Precision: x*w ~= xh*wh + xl*wh + xh*wl (3 bf16 MMAs, fp32 accumulate): the
+// dropped terms are O(2^-16) relative, i.e. fp32-grade for the 1e-3 parity
+// budget, where a single bf16 (5e-3) or tf32 (7e-4) pass is not.
+//
+// Replaces (reference file:line): bottleneck improved_sudormrf.py:256-259,292;
+// proj_1x1.conv :174,205; res_conv(+skip) :196,220; mask_net :268-269,295-298.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace sdr {
+
+constexpr int kTileM = 128;            // positions per tile (UMMA M, TMEM lanes)
+constexpr int kBlockK = 64;            // channels per k-block = one 128 B swizzle row of bf16
+constexpr int kStages = 2;
+constexpr int kMaxTileN = 256;         // output channels per tile (UMMA N, TMEM columns per stage)
+constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
+constexpr int kBHalfMax = kMaxTileN * 128;
+constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalfMax;      // 96 KB
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
+constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
+constexpr int kProdThreads = 32 * kProdWarps;                 // 256
+
+struct MmaArgs {
+    const float* x;
+    NormIn nin;
+    const uint8_t* wpk;        // packed weight images
+    const float* bias;
+    const float* residual;
+    const float* gate;
+    int gate_channels;
+    float* y;
+    double* stats_out;
+    int M, K, L;
+    int l_tiles, n_tiles, tile_n, num_tiles;
+    int epilogue;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp
+// documents the bit layout): start address >> 4 in [0,14), LBO (unused for swizzled
+// K-major, canonical value 1) in [16,30), SBO = 1024 B (8 rows x 128 B) in [32,46),
+// version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major,
+// N>>3 in [17,23), M>>4 in [24,29).
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+// weight packing: W[M][K] fp32 -> per (n_tile, k_block) a contiguous image
+// [hi: tile_n rows x 128 B | lo: tile_n rows x 128 B], rows swizzled exactly as
+// they must sit in shared memory (16 B chunk index XOR row%8).
+// ---------------------------------------------------------------------------
+__global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __restrict__ out,
+                                       int M, int K, int tile_n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 16 B chunk (8 k) per thread
+    const long long chunks = (long long)M * K / 8;
+    if (i >= chunks) return;
+    const int kc = (int)(i % (K / 8));        // chunk index along K
+    const int m = (int)(i / (K / 8));
+    const int kb = kc / 8, c = kc % 8;
+    const int nt = m / tile_n, r = m % tile_n;
+    const int KB = K / kBlockK;
+    const size_t half = (size_t)tile_n * 128;
+    uint8_t* img = out + ((size_t)nt * KB + kb) * 2 * half;
+    const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((c ^ (r & 7)) << 4);
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float v = W[(size_t)m * K + kc * 8 + e];
+        hi[e] = __float2bfloat16_rn(v);
+        lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
+    }
+    *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + half + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// ---------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------
+struct TileCoord { int sample, l0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
+    TileCoord t;
+    const int nt = tile % a.n_tiles;
+    const int rest = tile / a.n_tiles;
+    const int lt = rest % a.l_tiles;
+    t.sample = rest / a.l_tiles;
+    t.l0 = lt * kTileM;
+    t.n0 = nt * a.tile_n;
+    return t;
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1)
+pw_mma_kernel(const MmaArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;                                            // kStages x 96 KB
+    float2* s_ab = reinterpret_cast<float2*>(smem + kStages * kStageBytes);  // [kStages][64]
+    float* s_bias = reinterpret_cast<float*>(s_ab + kStages * kBlockK);      // [2][256]
+    SampleNorm* s_sn = reinterpret_cast<SampleNorm*>(s_bias + 2 * kMaxTileN);   // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sn + 2);
+    uint64_t* full_bar = bars;                     // [kStages]
+    uint64_t* empty_bar = bars + kStages;          // [kStages]
+    uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
+    uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int KB = a.K / kBlockK;
+    const uint32_t bhalf = (uint32_t)a.tile_n * 128;
+
+    if (warp == kTmaWarp && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp >= kProdWarp0) {
+        // ===================== A-operand transform producers =====================
+        const int pt = tid - kProdWarp0 * 32;      // 0..255
+        const int p = pt & 127;                    // tile row (position)
+        const int cg = pt >> 7;                    // chunk group: chunks 4cg .. 4cg+3
+        const uint32_t row_off = (uint32_t)(p >> 3) * 1024 + (uint32_t)(p & 7) * 128;
+        const bool has_norm = a.nin.stats != nullptr;
+        const bool has_act = a.nin.prelu != nullptr;
+        const float slope = has_act ? __ldg(a.nin.prelu) : 1.f;
+
+        int tile = blockIdx.x;
+        if (tile < a.num_tiles) {
+            // flattened (tile, kb) iteration with a one-step register prefetch
+            TileCoord tc = decode_tile(a, tile);
+            int kb = 0;
+            float v[32], w[32];
+            auto issue_loads = [&](float (&dst)[32], const TileCoord& t, int kblk) {
+                const int l = t.l0 + p;
+                const float* xs = a.x + ((size_t)t.sample * a.K + (size_t)kblk * kBlockK + cg * 32) * a.L + l;
+                if (l < a.L) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) dst[e] = __ldg(xs + (size_t)e * a.L);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) dst[e] = 0.f;
+                }
+            };
+            issue_loads(v, tc, 0);
+            uint32_t it = 0;
+            int cur_sample = -1;
+            while (true) {
+                // next coordinate
+                int ntile = tile, nkb = kb + 1;
+                TileCoord ntc = tc;
+                if (nkb == KB) { nkb = 0; ntile = tile + gridDim.x; if (ntile < a.num_tiles) ntc = decode_tile(a, ntile); }
+                const bool has_next = ntile < a.num_tiles;
+                if (has_next) issue_loads(w, ntc, nkb);
+
+                const int stage = it % kStages;
+                const uint32_t phase = (it / kStages) & 1;
+                // per-sample normalisation scalars (once per tile), per-k-block channel table
+                if (tc.sample != cur_sample) {
+                    if (pt == 0) s_sn[0] = sample_norm(a.nin, tc.sample);
+                    named_bar_sync(1, kProdThreads);
+                    cur_sample = tc.sample;
+                }
+                if (pt < kBlockK) {
+                    const int k = kb * kBlockK + pt;
+                    float aa = 1.f, bb = 0.f;
+                    if (has_norm) {
+                        const SampleNorm sn = s_sn[0];
+                        aa = __ldg(a.nin.gamma + k) * sn.rstd;
+                        bb = __ldg(a.nin.beta + k) - sn.mean * aa;
+                    }
+                    s_ab[stage * kBlockK + pt] = make_float2(aa, bb);
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                named_bar_sync(1, kProdThreads);
+
+                uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes;
+                uint8_t* a_lo = a_hi + kAHalf;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = cg * 4 + cc;
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const float2 ab0 = s_ab[stage * kBlockK + c * 8 + 2 * e2];
+                        const float2 ab1 = s_ab[stage * kBlockK + c * 8 + 2 * e2 + 1];
+                        float y0 = fmaf(v[cc * 8 + 2 * e2], ab0.x, ab0.y);
+                        float y1 = fmaf(v[cc * 8 + 2 * e2 + 1], ab1.x, ab1.y);
+                        if (has_act) {
+                            y0 = y0 >= 0.f ? y0 : y0 * slope;
+                            y1 = y1 >= 0.f ? y1 : y1 * slope;
+                        }
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 lw = __floats2bfloat162_rn(y0 - hf.x, y1 - hf.y);
+                        hi[e2] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[e2] = *reinterpret_cast<const uint32_t*>(&lw);
+                    }
+                    const uint32_t off = row_off + (uint32_t)((c ^ (p & 7)) << 4);
+                    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                ++it;
+                if (!has_next) break;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = w[e];
+                tile = ntile; kb = nkb; tc = ntc;
+            }
+        }
+    } else if (warp == kTmaWarp) {
+        // ===================== B-operand (weights) bulk-TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int nt = tile % a.n_tiles;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int stage = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], 2 * bhalf);
+                    const uint8_t* src = a.wpk + ((size_t)nt * KB + kb) * 2 * bhalf;
+                    uint8_t* dst = stage_base + (size_t)stage * kStageBytes + 2 * kAHalf;
+                    bulk_g2s(dst, src, 2 * bhalf, &full_bar[stage]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(a.tile_n);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
+                const int acc = ti & 1;
+                const uint32_t aphase = (ti >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxTileN;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int stage = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                    const uint32_t sa_lo = sa_hi + kAHalf;
+                    const uint32_t sb_hi = sa_hi + 2 * kAHalf;
+                    const uint32_t sb_lo = sb_hi + bhalf;
+#pragma unroll
+                    for (int ks = 0; ks < kBlockK / 16; ++ks) {
+                        const uint64_t dah = umma_desc_sw128(sa_hi + ks * 32);
+                        const uint64_t dal = umma_desc_sw128(sa_lo + ks * 32);
+                        const uint64_t dbh = umma_desc_sw128(sb_hi + ks * 32);
+                        const uint64_t dbl = umma_desc_sw128(sb_lo + ks * 32);
+                        umma_bf16(d_tmem, dah, dbh, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+                        umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);           // smem slot free once these MMAs retire
+                }
+                umma_commit(&tfull_bar[acc]);                 // accumulator ready for the epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp;                 // TMEM lane quarter of this warp
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
+            const int acc = ti & 1;
+            const uint32_t aphase = (ti >> 1) & 1;
+            const TileCoord tc = decode_tile(a, tile);
+            for (int j = tid; j < a.tile_n; j += kEpiWarps * 32)
+                s_bias[acc * kMaxTileN + j] = a.bias ? __ldg(a.bias + tc.n0 + j) : 0.f;
+            named_bar_sync(2, kEpiWarps * 32);
+            mbar_wait(&tfull_bar[acc], aphase);
+            tc_fence_after();
+            const int l = tc.l0 + q * 32 + lane;
+            const bool valid = l < a.L;
+            float st_s = 0.f, st_q = 0.f;
+            for (int c0 = 0; c0 < a.tile_n; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN + c0), r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = tc.n0 + c0 + j;
+                        const size_t idx = ((size_t)tc.sample * a.M + m) * a.L + l;
+                        float o = __uint_as_float(r[j]) + s_bias[acc * kMaxTileN + c0 + j];
+                        if (a.residual) o += a.residual[idx];
+                        if (a.epilogue == 1)
+                            o = fmaxf(o, 0.f) *
+                                __ldg(a.gate + ((size_t)tc.sample * a.gate_channels + (m % a.gate_channels)) * a.L + l);
+                        a.y[idx] = o;
+                        st_s += o; st_q = fmaf(o, o, st_q);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (a.stats_out) {
+                st_s = warp_sum(st_s);
+                st_q = warp_sum(st_q);
+                if (lane == 0) {
+                    atomicAdd(a.stats_out + 2 * (size_t)tc.sample, (double)st_s);
+                    atomicAdd(a.stats_out + 2 * (size_t)tc.sample + 1, (double)st_q);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static inline int mma_tile_n(int M) { return (M % 256 == 0) ? 256 : 128; }
+
+bool pointwise_mma_eligible(int M, int K) {
+    return M >= 128 && (M % 128) == 0 && K >= kBlockK && (K % kBlockK) == 0;
+}
+
+size_t pointwise_mma_packed_bytes(int M, int K) {
+    if (!pointwise_mma_eligible(M, K)) return 0;
+    return (size_t)M * K * 4;          // bf16 hi + bf16 lo per weight
+}
+
+int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t st) {
+    if (!pointwise_mma_eligible(M, K)) return SDR_ERR_UNSUPPORTED;
+    const long long chunks = (long long)M * K / 8;
+    pack_weight_mma_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(
+        W, static_cast<uint8_t*>(packed), M, K, mma_tile_n(M));
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+constexpr size_t kMmaSmemBytes = 1024 + (size_t)kStages * kStageBytes + kStages * kBlockK * sizeof(float2) +
+                                 2 * kMaxTileN * sizeof(float) + 2 * sizeof(SampleNorm) + 16 * sizeof(uint64_t);
+
+int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
+                         const float* residual, const float* gate, int gate_channels,
+                         float* y, double* stats_out, int samples, int M, int K, int L,
+                         int epilogue, cudaStream_t st) {
+    if (!pointwise_mma_eligible(M, K)) return SDR_ERR_UNSUPPORTED;
+    if (samples <= 0 || L <= 0 || !x || !wpk || !y) return SDR_ERR_BAD_ARGUMENT;
+    if (epilogue == 1 && (!gate || gate_channels <= 0)) return SDR_ERR_BAD_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(wpk) % 16) return SDR_ERR_BAD_ARGUMENT;
+    MmaArgs a;
+    a.x = x; a.nin = nin; a.wpk = static_cast<const uint8_t*>(wpk); a.bias = bias; a.residual = residual;
+    a.gate = gate; a.gate_channels = gate_channels; a.y = y; a.stats_out = stats_out;
+    a.M = M; a.K = K; a.L = L; a.epilogue = epilogue;
+    a.tile_n = mma_tile_n(M);
+    a.n_tiles = M / a.tile_n;
+    a.l_tiles = (L + kTileM - 1) / kTileM;
+    const long long tiles = (long long)samples * a.l_tiles * a.n_tiles;
+    if (tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    a.num_tiles = (int)tiles;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
+    if (cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
+        return SDR_ERR_CUDA;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    pw_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+}  // namespace sdr

@@ -245,3 +245,75 @@ def test_mixture_consistency(kind):
     close(got, O.mixture_consistency(est, mix, kind), tol=1e-5)
     if kind == "uniform":
         assert torch.allclose(got.sum(1, keepdim=True).cpu(), mix, atol=1e-5)
+
+
+@pytest.mark.parametrize("samples,M,K,L,mode", [
+    (2, 256, 512, 3200, "norm"),          # bottleneck (cfg 2)
+    (3, 512, 256, 640, "plain_stats"),    # proj_1x1: two 256-wide n-tiles
+    (2, 256, 512, 1280, "res"),           # res_conv + in-place skip
+    (2, 1024, 256, 384, "mask"),          # mask_net
+    (2, 128, 64, 200, "res"),             # single k-block, 128-wide tile, ragged last position tile
+    (1, 384, 192, 100, "plain_stats"),    # tile_n = 128 x 3, 3 k-blocks, L < 128
+    (5, 256, 128, 130, "norm"),           # more tiles than... positions spill into a 2nd tile
+    (40, 512, 512, 384, "plain_stats"),   # > 148 tiles: persistent CTAs loop, both TMEM stages reused
+])
+def test_pointwise_tensor_core(samples, M, K, L, mode):
+    """tcgen05 path (bf16x3 split, fp32 accumulate) against an fp64 reference."""
+    lib = N.lib()
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(samples, K, L, generator=g) + 0.5).to(DEV)
+    W = (torch.randn(M, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(M, generator=g).to(DEV)
+    gamma = (1 + 0.3 * torch.randn(K, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(K, generator=g)).to(DEV)
+    slope = torch.tensor([0.2], device=DEV)
+    stats_in = raw_stats(x).to(DEV)
+    nbytes = lib.sdr_pointwise_mma_packed_bytes(M, K)
+    assert nbytes == M * K * 4
+    wpk = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    N.check(lib.sdr_pointwise_mma_pack(p(W), M, K, p(wpk), stream()))
+    y = torch.full((samples, M, L), float("nan"), device=DEV)
+    st = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    residual = gate = None
+    gate_ch, epi = 0, 0
+    if mode == "norm":
+        nin = norm_in(stats_in, gamma, beta, None, K * L)
+        fx = ref_norm(x.double(), gamma.double(), beta.double())
+    elif mode == "res":
+        nin = norm_in(stats_in, gamma, beta, slope, K * L)
+        fx = ref_norm(x.double(), gamma.double(), beta.double(), slope.double())
+        residual = torch.randn(samples, M, L, generator=g).to(DEV)
+        y = residual.clone()
+    elif mode == "mask":
+        nin = norm_in(None, None, None, slope, 1.0)
+        fx = O.prelu1(x.double(), slope.double())
+        gate_ch = M // 2
+        gate = torch.randn(samples, gate_ch, L, generator=g).to(DEV)
+        epi = 1
+    else:
+        nin = norm_in()
+        fx = x.double()
+    want = torch.einsum("mk,skl->sml", W.double(), fx) + bias.double().view(1, -1, 1)
+    if mode == "res":
+        want = want + residual.double()
+    if mode == "mask":
+        idx = torch.arange(M, device=DEV) % gate_ch
+        want = torch.relu(want) * gate.double()[:, idx, :]
+    want_stats = mode == "plain_stats"
+    N.check(lib.sdr_pointwise_mma(p(x), C.byref(nin), p(wpk), p(bias), p(y) if mode == "res" else p(None),
+                                  p(gate), gate_ch, p(y), p(st) if want_stats else p(None),
+                                  samples, M, K, L, epi, stream()))
+    torch.cuda.synchronize()
+    e = O.parity_errors(y, want)
+    print("tensor-core pointwise", (samples, M, K, L, mode), "rel_max %.2e rel_l2 %.2e" % e)
+    assert max(e) < 5e-5, e
+    if want_stats:
+        check_stats(st, want.float(), rtol=3e-5)
+
+
+def test_pointwise_tensor_core_eligibility():
+    lib = N.lib()
+    assert lib.sdr_pointwise_mma_packed_bytes(42, 1024) == 0       # decoder GEMM stays on the FFMA kernel
+    assert lib.sdr_pointwise_mma_packed_bytes(32, 16) == 0         # group-communication blocks
+    assert lib.sdr_pointwise_mma_packed_bytes(256, 100) == 0
+    assert lib.sdr_pointwise_mma_packed_bytes(512, 256) == 512 * 256 * 4
