@@ -358,11 +358,23 @@ def time_dominant_kernel(w, B, stream, flush, dev):
     nin = N.SdrNormIn(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), slope.data_ptr(), float(K * L))
     sp = C.c_void_p(stream.cuda_stream)
 
+    nbytes = N.lib().sdr_pointwise_mma_packed_bytes(M, K)
+    wpk = None
+    if nbytes:
+        wpk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        N.check(N.lib().sdr_pointwise_mma_pack(C.c_void_p(Wt.data_ptr()), M, K, C.c_void_p(wpk.data_ptr()), sp))
+
     def launch():
-        N.check(N.lib().sdr_pointwise(
-            C.c_void_p(xin.data_ptr()), C.byref(nin), C.c_void_p(Wt.data_ptr()),
-            C.c_void_p(bias.data_ptr()), C.c_void_p(res.data_ptr()), C.c_void_p(0), 0,
-            C.c_void_p(res.data_ptr()), C.c_void_p(0), samples, M, K, L, 0, sp))
+        if wpk is not None:       # the path the forward takes for this shape (tcgen05)
+            N.check(N.lib().sdr_pointwise_mma(
+                C.c_void_p(xin.data_ptr()), C.byref(nin), C.c_void_p(wpk.data_ptr()),
+                C.c_void_p(bias.data_ptr()), C.c_void_p(res.data_ptr()), C.c_void_p(0), 0,
+                C.c_void_p(res.data_ptr()), C.c_void_p(0), samples, M, K, L, 0, sp))
+        else:
+            N.check(N.lib().sdr_pointwise(
+                C.c_void_p(xin.data_ptr()), C.byref(nin), C.c_void_p(Wt.data_ptr()),
+                C.c_void_p(bias.data_ptr()), C.c_void_p(res.data_ptr()), C.c_void_p(0), 0,
+                C.c_void_p(res.data_ptr()), C.c_void_p(0), samples, M, K, L, 0, sp))
 
     for _ in range(3):
         launch()
@@ -379,11 +391,12 @@ def time_dominant_kernel(w, B, stream, flush, dev):
     peak, peak_src = load_peaks()
     bytes_per_launch = B * am["res_bytes"]
     achieved = bytes_per_launch / (avg / 1e3) / 1e9
-    return {"kernel": "pointwise GEMM res_conv+skip (sdr_pointwise)", "bound": "hbm",
+    return {"kernel": "pointwise GEMM res_conv+skip (" + ("pw_mma_kernel, tcgen05 bf16x3" if wpk is not None else "pw_gemm_kernel, FFMA") + ")",
+            "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg,
-            "tflops_fp32": B * am["res_flops"] / (avg / 1e3) / 1e12,
+            "tflops_fp32_equivalent": B * am["res_flops"] / (avg / 1e3) / 1e12,
             "shape": {"samples": samples, "M": M, "K": K, "L": L}}
 
 

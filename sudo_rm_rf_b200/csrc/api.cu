@@ -121,7 +121,8 @@ static Layout make_layout(const sdr_config* c) {
         l.ub[i].proj_pk = add_pk(l.cib, l.cob);
         l.ub[i].res_pk = add_pk(l.cob, l.cib);
     }
-    l.mask_pk = add_pk(l.S * l.A * l.N, l.Co);
+    // the gated epilogue needs an output tile (128/256 channels) to stay inside one source's N basis rows
+    l.mask_pk = (l.N % 256 == 0) ? add_pk(l.S * l.A * l.N, l.Co) : 0;
     l.total = cur;
     l.ok = true;
     return l;

@@ -34,6 +34,7 @@ constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalfMax;      // 96 KB
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
+constexpr int kProdElems = kTileM * kBlockK / kProdThreads;  // 32 channels of one position per thread and k-block
 
 struct MmaArgs {
     const float* x;
@@ -120,6 +121,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp
@@ -188,12 +197,13 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
 __global__ void __launch_bounds__(kMmaThreads, 1)
 pw_mma_kernel(const MmaArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024 B alignment for SWIZZLE_128B; pointer arithmetic (not an integer round trip) so the
+    // compiler keeps the shared address space and emits LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;                                            // kStages x 96 KB
     float2* s_ab = reinterpret_cast<float2*>(smem + kStages * kStageBytes);  // [kStages][64]
     float* s_bias = reinterpret_cast<float*>(s_ab + kStages * kBlockK);      // [2][256]
-    SampleNorm* s_sn = reinterpret_cast<SampleNorm*>(s_bias + 2 * kMaxTileN);   // [2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sn + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * kMaxTileN);
     uint64_t* full_bar = bars;                     // [kStages]
     uint64_t* empty_bar = bars + kStages;          // [kStages]
     uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
@@ -218,97 +228,122 @@ pw_mma_kernel(const MmaArgs a) {
 
     if (warp >= kProdWarp0) {
         // ===================== A-operand transform producers =====================
-        const int pt = tid - kProdWarp0 * 32;      // 0..255
-        const int p = pt & 127;                    // tile row (position)
-        const int cg = pt >> 7;                    // chunk group: chunks 4cg .. 4cg+3
+        const int pt = tid - kProdWarp0 * 32;      // 0..kProdThreads-1
+        const int p = pt & 127;                    // tile row (position); lanes = consecutive positions
+        const int cg = pt >> 7;                    // channel group: kProdElems channels of the k-block
         const uint32_t row_off = (uint32_t)(p >> 3) * 1024 + (uint32_t)(p & 7) * 128;
         const bool has_norm = a.nin.stats != nullptr;
         const bool has_act = a.nin.prelu != nullptr;
         const float slope = has_act ? __ldg(a.nin.prelu) : 1.f;
+        const bool tab_thread = pt < kBlockK;      // these 64 threads build the per-k-block (scale, shift) table
+        const double inv_count = 1.0 / a.nin.count;
+        const size_t Ls = (size_t)a.L;
 
-        int tile = blockIdx.x;
-        if (tile < a.num_tiles) {
-            // flattened (tile, kb) iteration with a one-step register prefetch
-            TileCoord tc = decode_tile(a, tile);
-            int kb = 0;
-            float v[32], w[32];
-            auto issue_loads = [&](float (&dst)[32], const TileCoord& t, int kblk) {
-                const int l = t.l0 + p;
-                const float* xs = a.x + ((size_t)t.sample * a.K + (size_t)kblk * kBlockK + cg * 32) * a.L + l;
-                if (l < a.L) {
+        struct Cur { int tile, kb; TileCoord tc; };
+        // everything a step needs from global memory, fetched one step ahead into registers
+        struct Pre { float v[kProdElems]; float g, b; double s0, s1; };
+        auto advance = [&](Cur& c) {              // next (tile, k-block) of this CTA; tile >= num_tiles == end
+            if (++c.kb == KB) {
+                c.kb = 0;
+                c.tile += gridDim.x;
+                if (c.tile < a.num_tiles) c.tc = decode_tile(a, c.tile);
+            }
+        };
+        auto issue_loads = [&](Pre& d, const Cur& c) {
+            const int l = c.tc.l0 + p;
+            const bool live = c.tile < a.num_tiles;
+            if (live && l < a.L) {
+                const float* xs = a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + cg * kProdElems) * Ls + l;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) dst[e] = __ldg(xs + (size_t)e * a.L);
-                } else {
+                for (int e = 0; e < kProdElems; ++e) { d.v[e] = __ldg(xs); xs += Ls; }
+            } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) dst[e] = 0.f;
+                for (int e = 0; e < kProdElems; ++e) d.v[e] = 0.f;
+            }
+            d.g = 1.f; d.b = 0.f; d.s0 = 0.0; d.s1 = 1.0;
+            if (tab_thread && has_norm && live) {
+                const int k = c.kb * kBlockK + pt;
+                d.g = __ldg(a.nin.gamma + k);
+                d.b = __ldg(a.nin.beta + k);
+                if (c.kb == 0) {                   // new tile: its sample's (sum, sumsq)
+                    d.s0 = a.nin.stats[2 * (size_t)c.tc.sample];
+                    d.s1 = a.nin.stats[2 * (size_t)c.tc.sample + 1];
                 }
-            };
-            issue_loads(v, tc, 0);
-            uint32_t it = 0;
-            int cur_sample = -1;
+            }
+        };
+        uint32_t it = 0;
+        float mean = 0.f, rstd = 1.f;              // of the current tile's sample (table threads only)
+        auto process = [&](const Pre& d, const Cur& c) {
+            const int stage = it % kStages;
+            const uint32_t phase = (it / kStages) & 1;
+            if (tab_thread) {                      // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
+                float aa = 1.f, bb = 0.f;
+                if (has_norm) {
+                    if (c.kb == 0) {
+                        const double mu = d.s0 * inv_count;
+                        double var = d.s1 * inv_count - mu * mu;
+                        var = var < 0.0 ? 0.0 : var;
+                        mean = (float)mu;
+                        rstd = (float)(1.0 / sqrt(var + (double)kGlnEps));
+                    }
+                    aa = d.g * rstd;
+                    bb = d.b - mean * aa;
+                }
+                s_ab[stage * kBlockK + pt] = make_float2(aa, bb);
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            named_bar_sync(1, kProdThreads);       // table visible; also orders reuse of s_ab[stage]
+            uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes;
+            uint8_t* a_lo = a_hi + kAHalf;
+            const float4* tab = reinterpret_cast<const float4*>(s_ab + stage * kBlockK + cg * kProdElems);
+#pragma unroll
+            for (int cc = 0; cc < kProdElems / 8; ++cc) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const float4 ab = tab[cc * 4 + e2];                 // (a0, b0, a1, b1)
+                    float y0 = fmaf(d.v[cc * 8 + 2 * e2], ab.x, ab.y);
+                    float y1 = fmaf(d.v[cc * 8 + 2 * e2 + 1], ab.z, ab.w);
+                    if (has_act) {
+                        y0 = y0 >= 0.f ? y0 : y0 * slope;
+                        y1 = y1 >= 0.f ? y1 : y1 * slope;
+                    }
+                    // hi = top 16 bits (truncation), lo = bf16(y - hi): y - hi is exact in fp32, so
+                    // |y - hi - lo| <= 2^-9 |y - hi| <= 2^-16 |y|
+                    const uint32_t b0 = __float_as_uint(y0) & 0xffff0000u, b1 = __float_as_uint(y1) & 0xffff0000u;
+                    hi[e2] = __byte_perm(b0, b1, 0x7632);
+                    const __nv_bfloat162 lw = __floats2bfloat162_rn(y0 - __uint_as_float(b0), y1 - __uint_as_float(b1));
+                    lo[e2] = *reinterpret_cast<const uint32_t*>(&lw);
+                }
+                const int c8 = cg * (kProdElems / 8) + cc;              // 16 B chunk index within the 128 B row
+                const uint32_t off = row_off + (uint32_t)((c8 ^ (p & 7)) << 4);
+                *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            ++it;
+        };
+
+        Cur c0;
+        c0.tile = blockIdx.x; c0.kb = 0;
+        if (c0.tile < a.num_tiles) {
+            c0.tc = decode_tile(a, c0.tile);
+            // ping-pong register prefetch: the loads of step i+1 are in flight while step i is transformed
+            Pre pa, pb;
+            Cur c1 = c0;
+            issue_loads(pa, c0);
+            advance(c1);
             while (true) {
-                // next coordinate
-                int ntile = tile, nkb = kb + 1;
-                TileCoord ntc = tc;
-                if (nkb == KB) { nkb = 0; ntile = tile + gridDim.x; if (ntile < a.num_tiles) ntc = decode_tile(a, ntile); }
-                const bool has_next = ntile < a.num_tiles;
-                if (has_next) issue_loads(w, ntc, nkb);
-
-                const int stage = it % kStages;
-                const uint32_t phase = (it / kStages) & 1;
-                // per-sample normalisation scalars (once per tile), per-k-block channel table
-                if (tc.sample != cur_sample) {
-                    if (pt == 0) s_sn[0] = sample_norm(a.nin, tc.sample);
-                    named_bar_sync(1, kProdThreads);
-                    cur_sample = tc.sample;
-                }
-                if (pt < kBlockK) {
-                    const int k = kb * kBlockK + pt;
-                    float aa = 1.f, bb = 0.f;
-                    if (has_norm) {
-                        const SampleNorm sn = s_sn[0];
-                        aa = __ldg(a.nin.gamma + k) * sn.rstd;
-                        bb = __ldg(a.nin.beta + k) - sn.mean * aa;
-                    }
-                    s_ab[stage * kBlockK + pt] = make_float2(aa, bb);
-                }
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                named_bar_sync(1, kProdThreads);
-
-                uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes;
-                uint8_t* a_lo = a_hi + kAHalf;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c = cg * 4 + cc;
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const float2 ab0 = s_ab[stage * kBlockK + c * 8 + 2 * e2];
-                        const float2 ab1 = s_ab[stage * kBlockK + c * 8 + 2 * e2 + 1];
-                        float y0 = fmaf(v[cc * 8 + 2 * e2], ab0.x, ab0.y);
-                        float y1 = fmaf(v[cc * 8 + 2 * e2 + 1], ab1.x, ab1.y);
-                        if (has_act) {
-                            y0 = y0 >= 0.f ? y0 : y0 * slope;
-                            y1 = y1 >= 0.f ? y1 : y1 * slope;
-                        }
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                        const float2 hf = __bfloat1622float2(h);
-                        const __nv_bfloat162 lw = __floats2bfloat162_rn(y0 - hf.x, y1 - hf.y);
-                        hi[e2] = *reinterpret_cast<const uint32_t*>(&h);
-                        lo[e2] = *reinterpret_cast<const uint32_t*>(&lw);
-                    }
-                    const uint32_t off = row_off + (uint32_t)((c ^ (p & 7)) << 4);
-                    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
-                fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
-                ++it;
-                if (!has_next) break;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = w[e];
-                tile = ntile; kb = nkb; tc = ntc;
+                issue_loads(pb, c1);
+                process(pa, c0);
+                if (c1.tile >= a.num_tiles) break;
+                c0 = c1; advance(c0);
+                issue_loads(pa, c0);
+                process(pb, c1);
+                if (c0.tile >= a.num_tiles) break;
+                c1 = c0; advance(c1);
             }
         }
     } else if (warp == kTmaWarp) {
@@ -368,41 +403,79 @@ pw_mma_kernel(const MmaArgs a) {
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int q = warp;                 // TMEM lane quarter of this warp
+        const bool gated = a.epilogue == 1;
+        const bool do_stats = a.stats_out != nullptr;
+        const size_t Ls = (size_t)a.L;
+        const int nchunks = a.tile_n / 32;
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
             const TileCoord tc = decode_tile(a, tile);
-            for (int j = tid; j < a.tile_n; j += kEpiWarps * 32)
-                s_bias[acc * kMaxTileN + j] = a.bias ? __ldg(a.bias + tc.n0 + j) : 0.f;
+            float* const sb = s_bias + acc * kMaxTileN;
+            for (int j = tid; j < a.tile_n; j += kEpiWarps * 32) sb[j] = a.bias ? __ldg(a.bias + tc.n0 + j) : 0.f;
             named_bar_sync(2, kEpiWarps * 32);
-            mbar_wait(&tfull_bar[acc], aphase);
-            tc_fence_after();
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
+            const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0) * Ls + l;       // (m = n0, l)
+            // residual (may alias y: in-place skip connection) or gate operand of this tile
+            const float* extra = nullptr;
+            if (valid) {
+                if (gated) extra = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
+                else if (a.residual) extra = a.residual + out_row0;
+            }
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
             float st_s = 0.f, st_q = 0.f;
-            for (int c0 = 0; c0 < a.tile_n; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN + c0), r);
+
+            // 32-column chunks.  The extra operand does not depend on the accumulator, so its loads run
+            // one chunk ahead (EA/EB ping-pong, first chunk issued before the accumulator is complete);
+            // a chunk's extra loads are always issued before the stores of the chunk before it.
+            float EA[32], EB[32];
+            uint32_t R[32];
+            const float* ep = extra;
+            auto issue_ex = [&](float (&E)[32], int c) {
+                if (ep != nullptr && c < nchunks) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { E[j] = *ep; ep += Ls; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) E[j] = 0.f;
+                }
+            };
+            float* yp = a.y + out_row0;
+            auto process = [&](const float (&E)[32], int c) {
+                tmem_ld32(t_acc + (uint32_t)(c * 32), R);
                 tmem_ld_wait();
                 if (valid) {
+                    const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int m = tc.n0 + c0 + j;
-                        const size_t idx = ((size_t)tc.sample * a.M + m) * a.L + l;
-                        float o = __uint_as_float(r[j]) + s_bias[acc * kMaxTileN + c0 + j];
-                        if (a.residual) o += a.residual[idx];
-                        if (a.epilogue == 1)
-                            o = fmaxf(o, 0.f) *
-                                __ldg(a.gate + ((size_t)tc.sample * a.gate_channels + (m % a.gate_channels)) * a.L + l);
-                        a.y[idx] = o;
-                        st_s += o; st_q = fmaf(o, o, st_q);
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bv = b4[j4];
+                        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j4 * 4 + u;
+                            float o = __uint_as_float(R[j]) + bb[u];
+                            o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
+                            *yp = o;
+                            yp += Ls;
+                            if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
+                        }
                     }
                 }
+            };
+            issue_ex(EA, 0);
+            mbar_wait(&tfull_bar[acc], aphase);
+            tc_fence_after();
+            for (int c = 0; c < nchunks; c += 2) {
+                issue_ex(EB, c + 1);
+                process(EA, c);
+                issue_ex(EA, c + 2);
+                if (c + 1 < nchunks) process(EB, c + 1);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
-            if (a.stats_out) {
+            if (do_stats) {
                 st_s = warp_sum(st_s);
                 st_q = warp_sum(st_q);
                 if (lane == 0) {
@@ -444,7 +517,7 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
 }
 
 constexpr size_t kMmaSmemBytes = 1024 + (size_t)kStages * kStageBytes + kStages * kBlockK * sizeof(float2) +
-                                 2 * kMaxTileN * sizeof(float) + 2 * sizeof(SampleNorm) + 16 * sizeof(uint64_t);
+                                 2 * kMaxTileN * sizeof(float) + 16 * sizeof(uint64_t);
 
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
                          const float* residual, const float* gate, int gate_channels,
@@ -453,6 +526,7 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     if (!pointwise_mma_eligible(M, K)) return SDR_ERR_UNSUPPORTED;
     if (samples <= 0 || L <= 0 || !x || !wpk || !y) return SDR_ERR_BAD_ARGUMENT;
     if (epilogue == 1 && (!gate || gate_channels <= 0)) return SDR_ERR_BAD_ARGUMENT;
+    if (epilogue == 1 && (gate_channels % mma_tile_n(M)) != 0) return SDR_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(wpk) % 16) return SDR_ERR_BAD_ARGUMENT;
     MmaArgs a;
     a.x = x; a.nin = nin; a.wpk = static_cast<const uint8_t*>(wpk); a.bias = bias; a.residual = residual;
@@ -467,9 +541,9 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
+    const int grid = (int)(tiles < sms ? tiles : sms);
     if (cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
         return SDR_ERR_CUDA;
-    const int grid = (int)(tiles < sms ? tiles : sms);
     pw_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
