@@ -55,7 +55,7 @@ struct Layout {
     bool gc;
     size_t enc_w, ln_g, ln_be, bn_w, bn_b, mask_a, mask_w, mask_b, dec_w;
     size_t dec_wt;                // derived: decoder weight as [S*A*K, S*A*N]
-    size_t bn_pk, mask_pk;        // derived: tensor-core weight images (0 = not eligible)
+    size_t bn_pk, mask_pk, dec_pk; // derived: tensor-core weight images (0 = not eligible)
     std::vector<UBlockOff> ub;
     std::vector<TacOff> tac;
     std::vector<size_t> off, numel;   // per state_dict entry
@@ -123,6 +123,7 @@ static Layout make_layout(const sdr_config* c) {
     }
     // the gated epilogue needs an output tile (128/256 channels) to stay inside one source's N basis rows
     l.mask_pk = (l.N % 256 == 0) ? add_pk(l.S * l.A * l.N, l.Co) : 0;
+    l.dec_pk = add_pk(l.S * l.A * l.K, l.S * l.A * l.N);
     l.total = cur;
     l.ok = true;
     return l;
@@ -255,8 +256,8 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
                           e, l.N, masked, nullptr, B, l.S * l.A * l.N, l.Co, L, 1, st));
     }
     // decoder: frames = Wd^T masked, then overlap-add / crop / mixture consistency
-    SDR_TRY(launch_pointwise_ffma(masked, none, pk + l.dec_wt, nullptr, nullptr, nullptr, 0,
-                                  frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
+    SDR_TRY(pointwise(masked, none, pk + l.dec_wt, l.dec_pk ? pk + l.dec_pk : nullptr, nullptr, nullptr, nullptr, 0,
+                      frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
     const float* mix = (apply_mc && l.A == 1) ? mixture : nullptr;
     SDR_TRY(launch_overlap_add(frames, mix, out, B, l.S * l.A, l.K, L, T, st));
     return SDR_OK;
@@ -335,6 +336,7 @@ int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_pa
         if (l.ub[i].res_pk) SDR_TRY(pack_pointwise_mma(pk + l.ub[i].res_w, l.cob, l.cib, pk + l.ub[i].res_pk, st));
     }
     if (l.mask_pk) SDR_TRY(pack_pointwise_mma(pk + l.mask_w, l.S * l.A * l.N, l.Co, pk + l.mask_pk, st));
+    if (l.dec_pk) SDR_TRY(pack_pointwise_mma(pk + l.dec_wt, l.S * l.A * l.K, l.S * l.A * l.N, pk + l.dec_pk, st));
     return SDR_OK;
 }
 

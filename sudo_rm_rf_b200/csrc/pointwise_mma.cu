@@ -88,6 +88,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -156,9 +159,9 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
 // they must sit in shared memory (16 B chunk index XOR row%8).
 // ---------------------------------------------------------------------------
 __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __restrict__ out,
-                                       int M, int K, int tile_n) {
+                                       int M, int Mpad, int K, int tile_n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 16 B chunk (8 k) per thread
-    const long long chunks = (long long)M * K / 8;
+    const long long chunks = (long long)Mpad * K / 8;
     if (i >= chunks) return;
     const int kc = (int)(i % (K / 8));        // chunk index along K
     const int m = (int)(i / (K / 8));
@@ -171,7 +174,7 @@ __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __r
     __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float v = W[(size_t)m * K + kc * 8 + e];
+        const float v = m < M ? W[(size_t)m * K + kc * 8 + e] : 0.f;      // rows >= M are zero padding
         hi[e] = __float2bfloat16_rn(v);
         lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
     }
@@ -271,6 +274,16 @@ pw_mma_kernel(const MmaArgs a) {
                 }
             }
         };
+        // L2 prefetch of a step's activation tile: one 128 B line per (warp, channel) -> lane e takes
+        // channel e of this warp's 32-channel group.  Issued two steps ahead so that the register
+        // loads one step ahead are L2 hits (HBM latency x 32 KB in flight per SM was the limiter).
+        auto prefetch_step = [&](const Cur& c) {
+            if (c.tile < a.num_tiles) {
+                const int l = c.tc.l0 + (p & ~31);
+                if (l < a.L)
+                    prefetch_l2(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + cg * kProdElems + lane) * Ls + l);
+            }
+        };
         uint32_t it = 0;
         float mean = 0.f, rstd = 1.f;              // of the current tile's sample (table threads only)
         auto process = [&](const Pre& d, const Cur& c) {
@@ -332,14 +345,18 @@ pw_mma_kernel(const MmaArgs a) {
             c0.tc = decode_tile(a, c0.tile);
             // ping-pong register prefetch: the loads of step i+1 are in flight while step i is transformed
             Pre pa, pb;
-            Cur c1 = c0;
+            Cur c1 = c0, cp;
             issue_loads(pa, c0);
             advance(c1);
+            cp = c1;
+            prefetch_step(cp);
             while (true) {
+                advance(cp); prefetch_step(cp);          // cp = two steps ahead of the step being processed
                 issue_loads(pb, c1);
                 process(pa, c0);
                 if (c1.tile >= a.num_tiles) break;
                 c0 = c1; advance(c0);
+                advance(cp); prefetch_step(cp);
                 issue_loads(pa, c0);
                 process(pb, c1);
                 if (c0.tile >= a.num_tiles) break;
@@ -413,7 +430,9 @@ pw_mma_kernel(const MmaArgs a) {
             const uint32_t aphase = (ti >> 1) & 1;
             const TileCoord tc = decode_tile(a, tile);
             float* const sb = s_bias + acc * kMaxTileN;
-            for (int j = tid; j < a.tile_n; j += kEpiWarps * 32) sb[j] = a.bias ? __ldg(a.bias + tc.n0 + j) : 0.f;
+            const int ncols = min(a.tile_n, a.M - tc.n0);      // real output channels in this tile (< tile_n: padding)
+            for (int j = tid; j < a.tile_n; j += kEpiWarps * 32)
+                sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + j) : 0.f;
             named_bar_sync(2, kEpiWarps * 32);
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
@@ -426,6 +445,17 @@ pw_mma_kernel(const MmaArgs a) {
             }
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
             float st_s = 0.f, st_q = 0.f;
+            // pull this tile's residual / gate rows into L2 while the main loop runs: lane j of warp q
+            // takes the 128 B line (positions 32q..32q+31) of rows j, j+32, ...
+            if (gated || a.residual) {
+                const int lq = tc.l0 + q * 32;
+                if (lq < a.L) {
+                    const float* e0 = gated
+                        ? a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + lq
+                        : a.residual + ((size_t)tc.sample * a.M + tc.n0) * Ls + lq;
+                    for (int j = lane; j < ncols; j += 32) prefetch_l2(e0 + (size_t)j * Ls);
+                }
+            }
 
             // 32-column chunks.  The extra operand does not depend on the accumulator, so its loads run
             // one chunk ahead (EA/EB ping-pong, first chunk issued before the accumulator is complete);
@@ -434,9 +464,12 @@ pw_mma_kernel(const MmaArgs a) {
             uint32_t R[32];
             const float* ep = extra;
             auto issue_ex = [&](float (&E)[32], int c) {
-                if (ep != nullptr && c < nchunks) {
+                if (ep != nullptr && (c + 1) * 32 <= ncols) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { E[j] = *ep; ep += Ls; }
+                } else if (ep != nullptr && c * 32 < ncols) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { E[j] = (c * 32 + j < ncols) ? *ep : 0.f; ep += Ls; }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) E[j] = 0.f;
@@ -446,7 +479,8 @@ pw_mma_kernel(const MmaArgs a) {
             auto process = [&](const float (&E)[32], int c) {
                 tmem_ld32(t_acc + (uint32_t)(c * 32), R);
                 tmem_ld_wait();
-                if (valid) {
+                const int jmax = ncols - c * 32;               // >= 32 for a full chunk
+                if (valid && jmax > 0) {
                     const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -457,9 +491,11 @@ pw_mma_kernel(const MmaArgs a) {
                             const int j = j4 * 4 + u;
                             float o = __uint_as_float(R[j]) + bb[u];
                             o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
-                            *yp = o;
+                            if (j < jmax) {
+                                *yp = o;
+                                if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
+                            }
                             yp += Ls;
-                            if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
                         }
                     }
                 }
@@ -497,22 +533,26 @@ pw_mma_kernel(const MmaArgs a) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static inline int mma_tile_n(int M) { return (M % 256 == 0) ? 256 : 128; }
+static inline int mma_pad_m(int M) { return (M + 127) / 128 * 128; }
+static inline int mma_tile_n(int M) { return (mma_pad_m(M) % 256 == 0) ? 256 : 128; }
 
+// Output-channel counts that are not a multiple of 128 are zero-padded (decoder: 2*21 = 42 rows);
+// the reduction dimension must fill whole 64-channel k-blocks.
 bool pointwise_mma_eligible(int M, int K) {
-    return M >= 128 && (M % 128) == 0 && K >= kBlockK && (K % kBlockK) == 0;
+    return M >= 32 && K >= kBlockK && (K % kBlockK) == 0;
 }
 
 size_t pointwise_mma_packed_bytes(int M, int K) {
     if (!pointwise_mma_eligible(M, K)) return 0;
-    return (size_t)M * K * 4;          // bf16 hi + bf16 lo per weight
+    return (size_t)mma_pad_m(M) * K * 4;          // bf16 hi + bf16 lo per (padded) weight
 }
 
 int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t st) {
     if (!pointwise_mma_eligible(M, K)) return SDR_ERR_UNSUPPORTED;
-    const long long chunks = (long long)M * K / 8;
+    const int Mpad = mma_pad_m(M);
+    const long long chunks = (long long)Mpad * K / 8;
     pack_weight_mma_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(
-        W, static_cast<uint8_t*>(packed), M, K, mma_tile_n(M));
+        W, static_cast<uint8_t*>(packed), M, Mpad, K, mma_tile_n(M));
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
@@ -533,7 +573,7 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     a.gate = gate; a.gate_channels = gate_channels; a.y = y; a.stats_out = stats_out;
     a.M = M; a.K = K; a.L = L; a.epilogue = epilogue;
     a.tile_n = mma_tile_n(M);
-    a.n_tiles = M / a.tile_n;
+    a.n_tiles = mma_pad_m(M) / a.tile_n;
     a.l_tiles = (L + kTileM - 1) / kTileM;
     const long long tiles = (long long)samples * a.l_tiles * a.n_tiles;
     if (tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;

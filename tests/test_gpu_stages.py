@@ -57,6 +57,8 @@ def ref_norm(x, gamma, beta, prelu=None):
     (3, 32, 3200, 1, True), (2, 32, 3200, 2, False), (2, 16, 200, 2, False),
     (2, 24, 104, 1, True), (5, 7, 26, 1, False), (5, 7, 26, 2, False), (1, 3, 2, 2, False),
     (2, 512, 800, 2, False), (4, 5, 4, 1, True),
+    (2, 9, 16, 1, False), (2, 9, 16, 2, True), (3, 6, 8, 1, True), (2, 512, 3200, 1, True),
+    (2, 33, 6400, 2, False), (1, 4, 40, 1, False),
 ])
 def test_depthwise(samples, C_, L, stride, prelu):
     g = torch.Generator().manual_seed(0)
@@ -80,6 +82,7 @@ def test_depthwise(samples, C_, L, stride, prelu):
 
 @pytest.mark.parametrize("samples,C_,L,depth", [
     (2, 32, 3200, 5), (3, 16, 64, 6), (2, 8, 32, 1), (2, 5, 2, 1), (2, 6, 6, 2), (1, 512, 3200, 5),
+    (2, 8, 48, 4), (2, 7, 128, 8), (3, 5, 24, 4), (2, 512, 6400, 6),
 ])
 def test_merge(samples, C_, L, depth):
     g = torch.Generator().manual_seed(1)
@@ -256,6 +259,9 @@ def test_mixture_consistency(kind):
     (1, 384, 192, 100, "plain_stats"),    # tile_n = 128 x 3, 3 k-blocks, L < 128
     (5, 256, 128, 130, "norm"),           # more tiles than... positions spill into a 2nd tile
     (40, 512, 512, 384, "plain_stats"),   # > 148 tiles: persistent CTAs loop, both TMEM stages reused
+    (3, 42, 1024, 200, "plain"),          # decoder GEMM: 42 rows zero-padded to one 128-wide tile
+    (2, 300, 128, 333, "res"),            # 300 rows -> padded to 384 = 3 tiles of 128, last one partial
+    (2, 160, 64, 64, "plain_stats"),      # padded to 256: one 256-wide tile with 96 padding columns
 ])
 def test_pointwise_tensor_core(samples, M, K, L, mode):
     """tcgen05 path (bf16x3 split, fp32 accumulate) against an fp64 reference."""
@@ -269,7 +275,7 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
     slope = torch.tensor([0.2], device=DEV)
     stats_in = raw_stats(x).to(DEV)
     nbytes = lib.sdr_pointwise_mma_packed_bytes(M, K)
-    assert nbytes == M * K * 4
+    assert nbytes == (M + 127) // 128 * 128 * K * 4
     wpk = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     N.check(lib.sdr_pointwise_mma_pack(p(W), M, K, p(wpk), stream()))
     y = torch.full((samples, M, L), float("nan"), device=DEV)
@@ -313,7 +319,8 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
 
 def test_pointwise_tensor_core_eligibility():
     lib = N.lib()
-    assert lib.sdr_pointwise_mma_packed_bytes(42, 1024) == 0       # decoder GEMM stays on the FFMA kernel
+    assert lib.sdr_pointwise_mma_packed_bytes(42, 1024) == 128 * 1024 * 4   # decoder GEMM: rows padded to 128
+    assert lib.sdr_pointwise_mma_packed_bytes(16, 64) == 0
     assert lib.sdr_pointwise_mma_packed_bytes(32, 16) == 0         # group-communication blocks
     assert lib.sdr_pointwise_mma_packed_bytes(256, 100) == 0
     assert lib.sdr_pointwise_mma_packed_bytes(512, 256) == 512 * 256 * 4
