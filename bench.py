@@ -103,7 +103,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -217,13 +217,10 @@ def run_b200(args, w, wl_name):
         model.load_state_dict(O.make_state_dict(cfg_o, seed=0, perturbed=False))
     model = model.to(dev).eval()
     if world > 1:
-        # ONE broadcast of all weights over NVLink, outside the timed step
-        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()])
-        dist.broadcast(flat, src=0)
-        off = 0
-        for p in model.parameters():
-            p.data.copy_(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+        # ONE broadcast of all weights over NVLink (NCCL), outside the timed step; the step itself
+        # has no collective: every rank separates its own shard of the batch
+        from sudo_rm_rf_b200 import sharding
+        sharding.broadcast_parameters(model, src=0)
     cfg = _engine.make_config(model)
     launches_per_step = _native.lib().sdr_forward_launch_count(C.byref(cfg))
 

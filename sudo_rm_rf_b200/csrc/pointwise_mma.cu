@@ -26,11 +26,13 @@ namespace sdr {
 
 constexpr int kTileM = 128;            // positions per tile (UMMA M, TMEM lanes)
 constexpr int kBlockK = 64;            // channels per k-block = one 128 B swizzle row of bf16
-constexpr int kStages = 2;
+constexpr int kAStages = 2;            // activation (A) ring (a 3rd stage would use all 227 KB and starve L1: measured slower)
+constexpr int kBStages = 2;            // weight (B) ring
 constexpr int kMaxTileN = 256;         // output channels per tile (UMMA N, TMEM columns per stage)
 constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
 constexpr int kBHalfMax = kMaxTileN * 128;
-constexpr int kStageBytes = 2 * kAHalf + 2 * kBHalfMax;      // 96 KB
+constexpr int kAStageBytes = 2 * kAHalf;                     // 32 KB: hi + lo
+constexpr int kBStageBytes = 2 * kBHalfMax;                  // 64 KB: hi + lo
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
@@ -199,19 +201,22 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
 
 __global__ void __launch_bounds__(kMmaThreads, 1)
 pw_mma_kernel(const MmaArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    // 1024 B alignment for SWIZZLE_128B; pointer arithmetic (not an integer round trip) so the
-    // compiler keeps the shared address space and emits LDS/STS
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* stage_base = smem;                                            // kStages x 96 KB
-    float2* s_ab = reinterpret_cast<float2*>(smem + kStages * kStageBytes);  // [kStages][64]
-    float* s_bias = reinterpret_cast<float*>(s_ab + kStages * kBlockK);      // [2][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * kMaxTileN);
-    uint64_t* full_bar = bars;                     // [kStages]
-    uint64_t* empty_bar = bars + kStages;          // [kStages]
-    uint64_t* tfull_bar = bars + 2 * kStages;      // [2]
-    uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    // Exactly the 227 KB an sm_100 CTA can own: 3 x 32 KB A stages + 2 x 64 KB B stages + 2.7 KB of
+    // tables and barriers.  SWIZZLE_128B needs the stage bases 1024 B aligned.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* a_base = smem;                                                  // kAStages x 32 KB
+    uint8_t* b_base = smem + kAStages * kAStageBytes;                        // kBStages x 64 KB
+    float2* s_ab = reinterpret_cast<float2*>(b_base + kBStages * kBStageBytes);   // [kAStages][64]
+    float* s_bias = reinterpret_cast<float*>(s_ab + kAStages * kBlockK);     // [256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kMaxTileN);
+    uint64_t* fullA = bars;                          // [kAStages]
+    uint64_t* emptyA = fullA + kAStages;             // [kAStages]
+    uint64_t* fullB = emptyA + kAStages;             // [kBStages]
+    uint64_t* emptyB = fullB + kBStages;             // [kBStages]
+    uint64_t* tfull_bar = emptyB + kBStages;         // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -219,7 +224,8 @@ pw_mma_kernel(const MmaArgs a) {
     const uint32_t bhalf = (uint32_t)a.tile_n * 128;
 
     if (warp == kTmaWarp && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&fullA[s], kProdWarps); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < kBStages; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
         fence_barrier_init();
     }
@@ -287,8 +293,8 @@ pw_mma_kernel(const MmaArgs a) {
         uint32_t it = 0;
         float mean = 0.f, rstd = 1.f;              // of the current tile's sample (table threads only)
         auto process = [&](const Pre& d, const Cur& c) {
-            const int stage = it % kStages;
-            const uint32_t phase = (it / kStages) & 1;
+            const int stage = it % kAStages;
+            const uint32_t phase = (it / kAStages) & 1;
             if (tab_thread) {                      // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
                 float aa = 1.f, bb = 0.f;
                 if (has_norm) {
@@ -304,9 +310,9 @@ pw_mma_kernel(const MmaArgs a) {
                 }
                 s_ab[stage * kBlockK + pt] = make_float2(aa, bb);
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait(&emptyA[stage], phase ^ 1);
             named_bar_sync(1, kProdThreads);       // table visible; also orders reuse of s_ab[stage]
-            uint8_t* a_hi = stage_base + (size_t)stage * kStageBytes;
+            uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
             uint8_t* a_lo = a_hi + kAHalf;
             const float4* tab = reinterpret_cast<const float4*>(s_ab + stage * kBlockK + cg * kProdElems);
 #pragma unroll
@@ -335,7 +341,7 @@ pw_mma_kernel(const MmaArgs a) {
             }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (lane == 0) mbar_arrive(&fullA[stage]);
             ++it;
         };
 
@@ -370,13 +376,12 @@ pw_mma_kernel(const MmaArgs a) {
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 const int nt = tile % a.n_tiles;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int stage = it % kStages;
-                    const uint32_t phase = (it / kStages) & 1;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], 2 * bhalf);
+                    const int stage = it % kBStages;
+                    const uint32_t phase = (it / kBStages) & 1;
+                    mbar_wait(&emptyB[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&fullB[stage], 2 * bhalf);
                     const uint8_t* src = a.wpk + ((size_t)nt * KB + kb) * 2 * bhalf;
-                    uint8_t* dst = stage_base + (size_t)stage * kStageBytes + 2 * kAHalf;
-                    bulk_g2s(dst, src, 2 * bhalf, &full_bar[stage]);
+                    bulk_g2s(b_base + (size_t)stage * kBStageBytes, src, 2 * bhalf, &fullB[stage]);
                 }
             }
         }
@@ -393,13 +398,13 @@ pw_mma_kernel(const MmaArgs a) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxTileN;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int stage = it % kStages;
-                    const uint32_t phase = (it / kStages) & 1;
-                    mbar_wait(&full_bar[stage], phase);
+                    const int sa = it % kAStages, sb = it % kBStages;
+                    mbar_wait(&fullB[sb], (it / kBStages) & 1);
+                    mbar_wait(&fullA[sa], (it / kAStages) & 1);
                     tc_fence_after();
-                    const uint32_t sa_hi = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                    const uint32_t sa_hi = smem_u32(a_base + (size_t)sa * kAStageBytes);
                     const uint32_t sa_lo = sa_hi + kAHalf;
-                    const uint32_t sb_hi = sa_hi + 2 * kAHalf;
+                    const uint32_t sb_hi = smem_u32(b_base + (size_t)sb * kBStageBytes);
                     const uint32_t sb_lo = sb_hi + bhalf;
 #pragma unroll
                     for (int ks = 0; ks < kBlockK / 16; ++ks) {
@@ -411,7 +416,8 @@ pw_mma_kernel(const MmaArgs a) {
                         umma_bf16(d_tmem, dal, dbh, idesc, 1u);
                         umma_bf16(d_tmem, dah, dbl, idesc, 1u);
                     }
-                    umma_commit(&empty_bar[stage]);           // smem slot free once these MMAs retire
+                    umma_commit(&emptyA[sa]);                 // slots free once these MMAs retire
+                    umma_commit(&emptyB[sb]);
                 }
                 umma_commit(&tfull_bar[acc]);                 // accumulator ready for the epilogue
             }
@@ -429,8 +435,9 @@ pw_mma_kernel(const MmaArgs a) {
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
             const TileCoord tc = decode_tile(a, tile);
-            float* const sb = s_bias + acc * kMaxTileN;
+            float* const sb = s_bias;
             const int ncols = min(a.tile_n, a.M - tc.n0);      // real output channels in this tile (< tile_n: padding)
+            named_bar_sync(2, kEpiWarps * 32);                 // every warp is done with the previous tile's bias
             for (int j = tid; j < a.tile_n; j += kEpiWarps * 32)
                 sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + j) : 0.f;
             named_bar_sync(2, kEpiWarps * 32);
@@ -556,8 +563,10 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
-constexpr size_t kMmaSmemBytes = 1024 + (size_t)kStages * kStageBytes + kStages * kBlockK * sizeof(float2) +
-                                 2 * kMaxTileN * sizeof(float) + 16 * sizeof(uint64_t);
+constexpr size_t kMmaSmemBytes = (size_t)kAStages * kAStageBytes + (size_t)kBStages * kBStageBytes +
+                                 kAStages * kBlockK * sizeof(float2) + kMaxTileN * sizeof(float) +
+                                 (2 * kAStages + 2 * kBStages + 4 + 2) * sizeof(uint64_t);
+static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
                          const float* residual, const float* gate, int gate_channels,
