@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsudormrf_b200.so")
+LIB_PATH = os.environ.get("SDR_B200_LIB") or os.path.join(_HERE, "libsudormrf_b200.so")   # env override: A/B-testing kernel builds
 CSRC = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 1

@@ -26,8 +26,9 @@ namespace sdr {
 
 constexpr int kTileM = 128;            // positions per tile (UMMA M, TMEM lanes)
 constexpr int kBlockK = 64;            // channels per k-block = one 128 B swizzle row of bf16
-constexpr int kAStages = 2;            // activation (A) ring (a 3rd stage would use all 227 KB and starve L1: measured slower)
-constexpr int kBStages = 2;            // weight (B) ring
+constexpr int kAStages = 2;            // A (activation) and B (weight) stages share one full/empty barrier ring:
+constexpr int kBStages = 2;            // a tcgen05.commit per ring and k-block measured ~40 % slower than one
+static_assert(kAStages == kBStages, "one barrier ring");
 constexpr int kMaxTileN = 256;         // output channels per tile (UMMA N, TMEM columns per stage)
 constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
 constexpr int kBHalfMax = kMaxTileN * 128;
@@ -206,14 +207,14 @@ pw_mma_kernel(const MmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_base = smem;                                                  // kAStages x 32 KB
     uint8_t* b_base = smem + kAStages * kAStageBytes;                        // kBStages x 64 KB
-    float2* s_ab = reinterpret_cast<float2*>(b_base + kBStages * kBStageBytes);   // [kAStages][64]
-    float* s_bias = reinterpret_cast<float*>(s_ab + kAStages * kBlockK);     // [256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kMaxTileN);
-    uint64_t* fullA = bars;                          // [kAStages]
-    uint64_t* emptyA = fullA + kAStages;             // [kAStages]
-    uint64_t* fullB = emptyA + kAStages;             // [kBStages]
-    uint64_t* emptyB = fullB + kBStages;             // [kBStages]
-    uint64_t* tfull_bar = emptyB + kBStages;         // [2]
+    // warp-private tables (no CTA-level barrier in the steady state): per transform warp the
+    // (scale, shift) of its 32 channels, double-buffered; per epilogue warp a copy of the tile's bias
+    float2* s_ab = reinterpret_cast<float2*>(b_base + kBStages * kBStageBytes);   // [kProdWarps][2][32]
+    float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 2 * 32);    // [kEpiWarps][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kEpiWarps * kMaxTileN);
+    uint64_t* full_bar = bars;                       // [kAStages]  8 transform warps + the TMA thread (+tx bytes)
+    uint64_t* empty_bar = full_bar + kAStages;       // [kAStages]  one tcgen05.commit
+    uint64_t* tfull_bar = empty_bar + kAStages;      // [2]
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -224,8 +225,7 @@ pw_mma_kernel(const MmaArgs a) {
     const uint32_t bhalf = (uint32_t)a.tile_n * 128;
 
     if (warp == kTmaWarp && lane == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&fullA[s], kProdWarps); mbar_init(&emptyA[s], 1); }
-        for (int s = 0; s < kBStages; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&full_bar[s], kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
         fence_barrier_init();
     }
@@ -244,7 +244,8 @@ pw_mma_kernel(const MmaArgs a) {
         const bool has_norm = a.nin.stats != nullptr;
         const bool has_act = a.nin.prelu != nullptr;
         const float slope = has_act ? __ldg(a.nin.prelu) : 1.f;
-        const bool tab_thread = pt < kBlockK;      // these 64 threads build the per-k-block (scale, shift) table
+        static_assert(kProdElems == 32, "lane e of a transform warp owns channel e of the warp's 32-channel group");
+        float2* const my_tab = s_ab + (warp - kProdWarp0) * 64;   // this warp's [2][32] (scale, shift) table
         const double inv_count = 1.0 / a.nin.count;
         const size_t Ls = (size_t)a.L;
 
@@ -270,8 +271,8 @@ pw_mma_kernel(const MmaArgs a) {
                 for (int e = 0; e < kProdElems; ++e) d.v[e] = 0.f;
             }
             d.g = 1.f; d.b = 0.f; d.s0 = 0.0; d.s1 = 1.0;
-            if (tab_thread && has_norm && live) {
-                const int k = c.kb * kBlockK + pt;
+            if (has_norm && live) {                // lane e: gamma/beta of channel e of this warp's group
+                const int k = c.kb * kBlockK + cg * kProdElems + lane;
                 d.g = __ldg(a.nin.gamma + k);
                 d.b = __ldg(a.nin.beta + k);
                 if (c.kb == 0) {                   // new tile: its sample's (sum, sumsq)
@@ -291,11 +292,11 @@ pw_mma_kernel(const MmaArgs a) {
             }
         };
         uint32_t it = 0;
-        float mean = 0.f, rstd = 1.f;              // of the current tile's sample (table threads only)
+        float mean = 0.f, rstd = 1.f;              // of the current tile's sample
         auto process = [&](const Pre& d, const Cur& c) {
             const int stage = it % kAStages;
             const uint32_t phase = (it / kAStages) & 1;
-            if (tab_thread) {                      // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
+            {                                      // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
                 float aa = 1.f, bb = 0.f;
                 if (has_norm) {
                     if (c.kb == 0) {
@@ -308,13 +309,13 @@ pw_mma_kernel(const MmaArgs a) {
                     aa = d.g * rstd;
                     bb = d.b - mean * aa;
                 }
-                s_ab[stage * kBlockK + pt] = make_float2(aa, bb);
+                my_tab[(it & 1) * 32 + lane] = make_float2(aa, bb);
             }
-            mbar_wait(&emptyA[stage], phase ^ 1);
-            named_bar_sync(1, kProdThreads);       // table visible; also orders reuse of s_ab[stage]
+            __syncwarp();                          // table visible to the warp (reuse is ordered by the next __syncwarp)
+            mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
             uint8_t* a_lo = a_hi + kAHalf;
-            const float4* tab = reinterpret_cast<const float4*>(s_ab + stage * kBlockK + cg * kProdElems);
+            const float4* tab = reinterpret_cast<const float4*>(my_tab + (it & 1) * 32);
 #pragma unroll
             for (int cc = 0; cc < kProdElems / 8; ++cc) {
                 uint32_t hi[4], lo[4];
@@ -341,7 +342,7 @@ pw_mma_kernel(const MmaArgs a) {
             }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&fullA[stage]);
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
             ++it;
         };
 
@@ -378,10 +379,10 @@ pw_mma_kernel(const MmaArgs a) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int stage = it % kBStages;
                     const uint32_t phase = (it / kBStages) & 1;
-                    mbar_wait(&emptyB[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&fullB[stage], 2 * bhalf);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], 2 * bhalf);
                     const uint8_t* src = a.wpk + ((size_t)nt * KB + kb) * 2 * bhalf;
-                    bulk_g2s(b_base + (size_t)stage * kBStageBytes, src, 2 * bhalf, &fullB[stage]);
+                    bulk_g2s(b_base + (size_t)stage * kBStageBytes, src, 2 * bhalf, &full_bar[stage]);
                 }
             }
         }
@@ -398,9 +399,8 @@ pw_mma_kernel(const MmaArgs a) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxTileN;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int sa = it % kAStages, sb = it % kBStages;
-                    mbar_wait(&fullB[sb], (it / kBStages) & 1);
-                    mbar_wait(&fullA[sa], (it / kAStages) & 1);
+                    const int sa = it % kAStages, sb = sa;
+                    mbar_wait(&full_bar[sa], (it / kAStages) & 1);
                     tc_fence_after();
                     const uint32_t sa_hi = smem_u32(a_base + (size_t)sa * kAStageBytes);
                     const uint32_t sa_lo = sa_hi + kAHalf;
@@ -416,8 +416,7 @@ pw_mma_kernel(const MmaArgs a) {
                         umma_bf16(d_tmem, dal, dbh, idesc, 1u);
                         umma_bf16(d_tmem, dah, dbl, idesc, 1u);
                     }
-                    umma_commit(&emptyA[sa]);                 // slots free once these MMAs retire
-                    umma_commit(&emptyB[sb]);
+                    umma_commit(&empty_bar[sa]);              // both slots free once these MMAs retire
                 }
                 umma_commit(&tfull_bar[acc]);                 // accumulator ready for the epilogue
             }
@@ -435,12 +434,12 @@ pw_mma_kernel(const MmaArgs a) {
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
             const TileCoord tc = decode_tile(a, tile);
-            float* const sb = s_bias;
+            float* const sb = s_bias + q * kMaxTileN;          // this warp's private copy of the tile's bias
             const int ncols = min(a.tile_n, a.M - tc.n0);      // real output channels in this tile (< tile_n: padding)
-            named_bar_sync(2, kEpiWarps * 32);                 // every warp is done with the previous tile's bias
-            for (int j = tid; j < a.tile_n; j += kEpiWarps * 32)
+            __syncwarp();                                      // the warp is done with the previous tile's bias
+            for (int j = lane; j < a.tile_n; j += 32)
                 sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + j) : 0.f;
-            named_bar_sync(2, kEpiWarps * 32);
+            __syncwarp();
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
             const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0) * Ls + l;       // (m = n0, l)
@@ -470,11 +469,12 @@ pw_mma_kernel(const MmaArgs a) {
             float EA[32], EB[32];
             uint32_t R[32];
             const float* ep = extra;
+            const bool full_tile = ncols == a.tile_n;          // no zero-padded output channels in this tile
             auto issue_ex = [&](float (&E)[32], int c) {
-                if (ep != nullptr && (c + 1) * 32 <= ncols) {
+                if (ep != nullptr && c < nchunks && (full_tile || (c + 1) * 32 <= ncols)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { E[j] = *ep; ep += Ls; }
-                } else if (ep != nullptr && c * 32 < ncols) {
+                } else if (ep != nullptr && c * 32 < ncols) {       // partially padded chunk
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { E[j] = (c * 32 + j < ncols) ? *ep : 0.f; ep += Ls; }
                 } else {
@@ -487,8 +487,9 @@ pw_mma_kernel(const MmaArgs a) {
                 tmem_ld32(t_acc + (uint32_t)(c * 32), R);
                 tmem_ld_wait();
                 const int jmax = ncols - c * 32;               // >= 32 for a full chunk
-                if (valid && jmax > 0) {
-                    const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
+                if (!valid || jmax <= 0) return;
+                const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
+                if (jmax >= 32) {                              // fast path: no per-column predicate
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 bv = b4[j4];
@@ -498,12 +499,21 @@ pw_mma_kernel(const MmaArgs a) {
                             const int j = j4 * 4 + u;
                             float o = __uint_as_float(R[j]) + bb[u];
                             o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
-                            if (j < jmax) {
-                                *yp = o;
-                                if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
-                            }
+                            *yp = o;
                             yp += Ls;
+                            if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
                         }
+                    }
+                } else {                                       // last, partially padded chunk of a padded tile
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float o = __uint_as_float(R[j]) + sb[c * 32 + j];
+                        o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
+                        if (j < jmax) {
+                            *yp = o;
+                            if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
+                        }
+                        yp += Ls;
                     }
                 }
             };
@@ -564,8 +574,8 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
 }
 
 constexpr size_t kMmaSmemBytes = (size_t)kAStages * kAStageBytes + (size_t)kBStages * kBStageBytes +
-                                 kAStages * kBlockK * sizeof(float2) + kMaxTileN * sizeof(float) +
-                                 (2 * kAStages + 2 * kBStages + 4 + 2) * sizeof(uint64_t);
+                                 kProdWarps * 2 * 32 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
+                                 (2 * kAStages + 4 + 2) * sizeof(uint64_t);
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,

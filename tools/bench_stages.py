@@ -58,6 +58,23 @@ def timeit(name, fn, nbytes, flops=0.0):
                       "TFLOPs": round(flops / t / 1e9, 1)}), flush=True)
 
 
+# per-box normaliser: device-to-device copy bandwidth (same definition as MEASURED_PEAKS.json) + clocks
+import subprocess
+_a = torch.empty(1 << 30, dtype=torch.uint8, device=dev); _b = torch.empty_like(_a)
+for _ in range(3): _b.copy_(_a)
+best = 1e9
+for _ in range(10):
+    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_.record(st); _b.copy_(_a); e_.record(st); torch.cuda.synchronize()
+    best = min(best, s_.elapsed_time(e_))
+try:
+    smi = subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.mem,power.draw,temperature.gpu,uuid",
+                          "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+except Exception:
+    smi = "?"
+print(json.dumps({"box_copy_GBps": round(2 * (1 << 30) / best / 1e6, 1), "peak_file_GBps": peak, "nvidia_smi": smi}), flush=True)
+del _a, _b
+
 ones = lambda n: torch.ones(n, device=dev)
 zeros = lambda n: torch.zeros(n, device=dev)
 slope = torch.full((1,), 0.25, device=dev)
