@@ -136,6 +136,14 @@ typedef struct {
 int sdr_encoder(const float* wav, const float* weight, float* enc, double* stats,
                 int B, int A, int64_t T, int N, int K, int L, sdr_stream stream);
 
+/* The same encoder on the tensor cores: the tcgen05 GEMM kernel with a "window" operand producer
+ * (A[position, tap] = wav[hop*position + tap - pad], built in registers: no im2col in HBM); the
+ * weight is converted once to pre-swizzled bf16 hi/lo images (taps zero-padded to 64).  N >= 32. */
+size_t sdr_encoder_mma_packed_bytes(int N, int A, int K);
+int sdr_encoder_mma_pack(const float* weight, int N, int A, int K, void* packed, sdr_stream stream);
+int sdr_encoder_mma(const float* wav, const void* packed_w, float* enc, double* stats,
+                    int B, int A, int64_t T, int N, int K, int L, sdr_stream stream);
+
 /* 1x1 Conv1d as a GEMM: y[b,m,l] = sum_k W[m,k] f(x[b,k,l]) + bias[m]
  * (+ residual[b,m,l]); f = deferred norm/PReLU.  epilogue 0: plain,
  * 1: relu(y) * gate[b, m % gate_channels, l] (mask path, improved_sudormrf.py:296-298).

@@ -62,6 +62,10 @@ _SIGNATURES = {
                                           C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "sdr_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                               C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sdr_encoder_mma_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "sdr_encoder_mma_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "sdr_encoder_mma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sdr_pointwise": (C.c_int, [C.c_void_p, C.POINTER(SdrNormIn), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

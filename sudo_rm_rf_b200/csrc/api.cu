@@ -27,6 +27,10 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t)
 int launch_pointwise_mma(const float*, const NormIn&, const void*, const float*, const float*, const float*, int,
                          float*, double*, int, int, int, int, int, cudaStream_t);
 
+size_t encoder_mma_packed_bytes(int N, int A, int Kk);
+int pack_encoder_mma(const float* W, int N, int A, int Kk, void* packed, cudaStream_t);
+int launch_encoder_mma(const float*, const void*, float*, double*, int, int, long long, int, int, int, cudaStream_t);
+
 // One 1x1 convolution: tensor cores when the channel counts fill a tcgen05 tile, FFMA otherwise.
 static int pointwise(const float* x, const NormIn& nin, const float* W, const float* wpk, const float* bias,
                      const float* residual, const float* gate, int gate_channels, float* y, double* stats,
@@ -55,7 +59,7 @@ struct Layout {
     bool gc;
     size_t enc_w, ln_g, ln_be, bn_w, bn_b, mask_a, mask_w, mask_b, dec_w;
     size_t dec_wt;                // derived: decoder weight as [S*A*K, S*A*N]
-    size_t bn_pk, mask_pk, dec_pk; // derived: tensor-core weight images (0 = not eligible)
+    size_t bn_pk, mask_pk, dec_pk, enc_pk; // derived: tensor-core weight images (0 = not eligible)
     std::vector<UBlockOff> ub;
     std::vector<TacOff> tac;
     std::vector<size_t> off, numel;   // per state_dict entry
@@ -124,6 +128,11 @@ static Layout make_layout(const sdr_config* c) {
     // the gated epilogue needs an output tile (128/256 channels) to stay inside one source's N basis rows
     l.mask_pk = (l.N % 256 == 0) ? add_pk(l.S * l.A * l.N, l.Co) : 0;
     l.dec_pk = add_pk(l.S * l.A * l.K, l.S * l.A * l.N);
+    {
+        const size_t b = encoder_mma_packed_bytes(l.N, l.A, l.K);
+        l.enc_pk = b ? cur : 0;
+        cur += b / sizeof(float);
+    }
     l.total = cur;
     l.ok = true;
     return l;
@@ -197,7 +206,8 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
 
     // front end: encoder (+stats), ln folded into the bottleneck's operand load
-    SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, st));
+    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, slot(0), B, l.A, T, l.N, l.K, L, st));
+    else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, st));
     {
         NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)l.N * L};
         SDR_TRY(pointwise(e, ln, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
@@ -337,6 +347,7 @@ int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_pa
     }
     if (l.mask_pk) SDR_TRY(pack_pointwise_mma(pk + l.mask_w, l.S * l.A * l.N, l.Co, pk + l.mask_pk, st));
     if (l.dec_pk) SDR_TRY(pack_pointwise_mma(pk + l.dec_wt, l.S * l.A * l.K, l.S * l.A * l.N, pk + l.dec_pk, st));
+    if (l.enc_pk) SDR_TRY(pack_encoder_mma(pk + l.enc_w, l.N, l.A, l.K, pk + l.enc_pk, st));
     return SDR_OK;
 }
 
@@ -416,6 +427,20 @@ int sdr_encoder(const float* wav, const float* weight, float* enc, double* stats
     if (!wav || !weight || !enc || !stats) return SDR_ERR_BAD_ARGUMENT;
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
     return launch_encoder(wav, weight, enc, stats, B, A, T, N, K, L, static_cast<cudaStream_t>(stream));
+}
+
+size_t sdr_encoder_mma_packed_bytes(int N, int A, int K) { return encoder_mma_packed_bytes(N, A, K); }
+
+int sdr_encoder_mma_pack(const float* weight, int N, int A, int K, void* packed, sdr_stream stream) {
+    if (!weight || !packed) return SDR_ERR_BAD_ARGUMENT;
+    if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
+    return pack_encoder_mma(weight, N, A, K, packed, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_encoder_mma(const float* wav, const void* packed_w, float* enc, double* stats,
+                    int B, int A, int64_t T, int N, int K, int L, sdr_stream stream) {
+    if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
+    return launch_encoder_mma(wav, packed_w, enc, stats, B, A, T, N, K, L, static_cast<cudaStream_t>(stream));
 }
 
 int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const float* bias,

@@ -193,6 +193,101 @@ pw_gemm_kernel(const PwArgs a) {
     if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
 }
 
+
+// ---------------------------------------------------------------------------
+// Small-channel variant (group-communication blocks: 16 -> 32 and 32 -> 16 channels per
+// group, groupcomm_sudormrf_v2.py:401-403).  The op is pure streaming (AI ~ 4 FLOP/B), so the
+// tiled GEMM above wastes its tile; here a thread owns 4 consecutive positions x 16 output
+// channels: per input channel ONE float4 load (lanes = consecutive position quads -> 512 B per
+// warp), 64 FMAs against 16 weights broadcast from shared memory, float4 stores.
+// Requires K <= 64, L % 4 == 0.
+// ---------------------------------------------------------------------------
+constexpr int kSmThreads = 256;
+constexpr int kSmMT = 16;          // output channels per thread
+constexpr int kSmMaxK = 64;
+
+__global__ void __launch_bounds__(kSmThreads)
+pw_small_kernel(const PwArgs a, int chunks_per_sample) {
+    __shared__ __align__(16) float sW[kSmMaxK][kSmMT];     // [k][m]
+    __shared__ float2 sAB[kSmMaxK];                         // folded norm: y = x*a + b
+    __shared__ float sBias[kSmMT];
+    __shared__ float s_red[64];
+    const int tid = threadIdx.x;
+    const int sample = blockIdx.x / chunks_per_sample;
+    const int chunk = blockIdx.x - sample * chunks_per_sample;
+    const int m0 = blockIdx.y * kSmMT;
+    for (int i = tid; i < a.K * kSmMT; i += kSmThreads) {
+        const int k = i / kSmMT, m = i - k * kSmMT;
+        sW[k][m] = (m0 + m < a.M) ? __ldg(a.W + (size_t)(m0 + m) * a.K + k) : 0.f;
+    }
+    if (tid < kSmMT) sBias[tid] = (a.bias && m0 + tid < a.M) ? __ldg(a.bias + m0 + tid) : 0.f;
+    if (tid < a.K) {
+        float aa = 1.f, bb = 0.f;
+        if (a.nin.stats) {
+            const SampleNorm sn = sample_norm(a.nin, sample);
+            aa = __ldg(a.nin.gamma + tid) * sn.rstd;
+            bb = fmaf(-sn.mean, aa, __ldg(a.nin.beta + tid));
+        }
+        sAB[tid] = make_float2(aa, bb);
+    }
+    const bool act = a.nin.prelu != nullptr;
+    const float slope = act ? __ldg(a.nin.prelu) : 1.f;
+    __syncthreads();
+
+    const int QR = a.L >> 2;
+    const int q = chunk * kSmThreads + tid;
+    float st_s = 0.f, st_q = 0.f;
+    if (q < QR) {
+        const float* xp = a.x + (size_t)sample * a.K * a.L + 4 * q;
+        float acc[kSmMT][4];
+#pragma unroll
+        for (int m = 0; m < kSmMT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = sBias[m]; }
+#pragma unroll 4
+        for (int k = 0; k < a.K; ++k) {
+            float4 v = ldg4(xp + (size_t)k * a.L);
+            const float2 ab = sAB[k];
+            v.x = fmaf(v.x, ab.x, ab.y); v.y = fmaf(v.y, ab.x, ab.y);
+            v.z = fmaf(v.z, ab.x, ab.y); v.w = fmaf(v.w, ab.x, ab.y);
+            if (act) {
+                v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope;
+                v.z = v.z >= 0.f ? v.z : v.z * slope; v.w = v.w >= 0.f ? v.w : v.w * slope;
+            }
+#pragma unroll
+            for (int m4 = 0; m4 < kSmMT / 4; ++m4) {
+                const float4 w = *reinterpret_cast<const float4*>(&sW[k][m4 * 4]);
+                const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[m4 * 4 + u][0] = fmaf(ww[u], v.x, acc[m4 * 4 + u][0]);
+                    acc[m4 * 4 + u][1] = fmaf(ww[u], v.y, acc[m4 * 4 + u][1]);
+                    acc[m4 * 4 + u][2] = fmaf(ww[u], v.z, acc[m4 * 4 + u][2]);
+                    acc[m4 * 4 + u][3] = fmaf(ww[u], v.w, acc[m4 * 4 + u][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kSmMT; ++m) {
+            if (m0 + m < a.M) {
+                const size_t idx = ((size_t)sample * a.M + m0 + m) * a.L + 4 * q;
+                float o[4] = {acc[m][0], acc[m][1], acc[m][2], acc[m][3]};
+                if (a.residual) {
+                    const float4 r = *reinterpret_cast<const float4*>(a.residual + idx);   // may alias y
+                    o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+                }
+                if (a.epilogue == 1) {
+                    const float4 g = ldg4(a.gate + ((size_t)sample * a.gate_channels + ((m0 + m) % a.gate_channels)) * a.L + 4 * q);
+                    o[0] = fmaxf(o[0], 0.f) * g.x; o[1] = fmaxf(o[1], 0.f) * g.y;
+                    o[2] = fmaxf(o[2], 0.f) * g.z; o[3] = fmaxf(o[3], 0.f) * g.w;
+                }
+                *reinterpret_cast<float4*>(a.y + idx) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { st_s += o[e]; st_q = fmaf(o[e], o[e], st_q); }
+            }
+        }
+    }
+    if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
+}
+
 template <int BM>
 static int launch_bm(const PwArgs& a, int samples, bool vec, cudaStream_t st) {
     const long long gx = (long long)a.l_tiles * samples;
@@ -218,6 +313,14 @@ int launch_pointwise_ffma(const float* x, const NormIn& nin, const float* W, con
     if (residual) al |= reinterpret_cast<uintptr_t>(residual);
     if (gate) al |= reinterpret_cast<uintptr_t>(gate);
     const bool vec = (L % 4 == 0) && (al % 16 == 0);
+    if (vec && K <= kSmMaxK && M <= 64) {                 // streaming small-channel kernel
+        const int chunks = (L / 4 + kSmThreads - 1) / kSmThreads;
+        const long long gx = (long long)chunks * samples;
+        if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)gx, (unsigned)((M + kSmMT - 1) / kSmMT));
+        pw_small_kernel<<<grid, kSmThreads, 0, st>>>(a, chunks);
+        return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+    }
     if (M > 64) return launch_bm<128>(a, samples, vec, st);
     if (M > 32) return launch_bm<64>(a, samples, vec, st);
     return launch_bm<32>(a, samples, vec, st);

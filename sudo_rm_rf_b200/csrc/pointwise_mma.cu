@@ -52,6 +52,11 @@ struct MmaArgs {
     int M, K, L;
     int l_tiles, n_tiles, tile_n, num_tiles;
     int epilogue;
+    // window mode (encoder Conv1d as a GEMM without im2col): operand element (position p, k = a*win_k + j)
+    // is wav[sample, a, win_hop * p + j - win_pad] (zero outside [0, win_T)); x = wav, K = padded taps
+    int win_k;            // 0 = normal pointwise mode
+    int win_hop, win_pad, win_a;
+    long long win_T;
 };
 
 // ---------------------------------------------------------------------------
@@ -162,7 +167,7 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
 // they must sit in shared memory (16 B chunk index XOR row%8).
 // ---------------------------------------------------------------------------
 __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __restrict__ out,
-                                       int M, int Mpad, int K, int tile_n) {
+                                       int M, int Mpad, int Kreal, int K, int tile_n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 16 B chunk (8 k) per thread
     const long long chunks = (long long)Mpad * K / 8;
     if (i >= chunks) return;
@@ -177,7 +182,8 @@ __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __r
     __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float v = m < M ? W[(size_t)m * K + kc * 8 + e] : 0.f;      // rows >= M are zero padding
+        const int k = kc * 8 + e;                                          // rows >= M, taps >= Kreal: zero padding
+        const float v = (m < M && k < Kreal) ? W[(size_t)m * Kreal + k] : 0.f;
         hi[e] = __float2bfloat16_rn(v);
         lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi[e]));
     }
@@ -200,6 +206,9 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
     return t;
 }
 
+// WINDOW = true: encoder mode (strided waveform windows as the A operand), a separate instantiation so
+// the pointwise kernel's register allocation is unaffected.
+template <bool WINDOW>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 pw_mma_kernel(const MmaArgs a) {
     // Exactly the 227 KB an sm_100 CTA can own: 3 x 32 KB A stages + 2 x 64 KB B stages + 2.7 KB of
@@ -262,7 +271,17 @@ pw_mma_kernel(const MmaArgs a) {
         auto issue_loads = [&](Pre& d, const Cur& c) {
             const int l = c.tc.l0 + p;
             const bool live = c.tile < a.num_tiles;
-            if (live && l < a.L) {
+            if constexpr (WINDOW) {                // encoder: strided analysis windows of the waveform
+                const long long t0 = (long long)a.win_hop * l - a.win_pad;
+#pragma unroll
+                for (int e = 0; e < kProdElems; ++e) {
+                    const int k = c.kb * kBlockK + cg * kProdElems + e;
+                    const int ch = k / a.win_k, j = k - ch * a.win_k;
+                    const long long t = t0 + j;
+                    d.v[e] = (live && l < a.L && ch < a.win_a && t >= 0 && t < a.win_T)
+                                 ? __ldg(a.x + ((size_t)c.tc.sample * a.win_a + ch) * a.win_T + t) : 0.f;
+                }
+            } else if (live && l < a.L) {   // (pointwise mode)
                 const float* xs = a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + cg * kProdElems) * Ls + l;
 #pragma unroll
                 for (int e = 0; e < kProdElems; ++e) { d.v[e] = __ldg(xs); xs += Ls; }
@@ -285,7 +304,7 @@ pw_mma_kernel(const MmaArgs a) {
         // channel e of this warp's 32-channel group.  Issued two steps ahead so that the register
         // loads one step ahead are L2 hits (HBM latency x 32 KB in flight per SM was the limiter).
         auto prefetch_step = [&](const Cur& c) {
-            if (c.tile < a.num_tiles) {
+            if (!WINDOW && c.tile < a.num_tiles) {
                 const int l = c.tc.l0 + (p & ~31);
                 if (l < a.L)
                     prefetch_l2(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + cg * kProdElems + lane) * Ls + l);
@@ -569,7 +588,7 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
     const int Mpad = mma_pad_m(M);
     const long long chunks = (long long)Mpad * K / 8;
     pack_weight_mma_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(
-        W, static_cast<uint8_t*>(packed), M, Mpad, K, mma_tile_n(M));
+        W, static_cast<uint8_t*>(packed), M, Mpad, K, K, mma_tile_n(M));
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
@@ -591,6 +610,7 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     a.x = x; a.nin = nin; a.wpk = static_cast<const uint8_t*>(wpk); a.bias = bias; a.residual = residual;
     a.gate = gate; a.gate_channels = gate_channels; a.y = y; a.stats_out = stats_out;
     a.M = M; a.K = K; a.L = L; a.epilogue = epilogue;
+    a.win_k = 0; a.win_hop = 0; a.win_pad = 0; a.win_a = 0; a.win_T = 0;
     a.tile_n = mma_tile_n(M);
     a.n_tiles = mma_pad_m(M) / a.tile_n;
     a.l_tiles = (L + kTileM - 1) / kTileM;
@@ -601,9 +621,52 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    if (cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(pw_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
         return SDR_ERR_CUDA;
-    pw_mma_kernel<<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+    pw_mma_kernel<false><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+// ---- encoder on the same kernel (window mode) ----
+static inline int enc_kpad(int A, int Kk) { return (A * Kk + kBlockK - 1) / kBlockK * kBlockK; }
+
+size_t encoder_mma_packed_bytes(int N, int A, int Kk) {
+    if (N < 32 || A < 1 || Kk < 3) return 0;
+    return (size_t)mma_pad_m(N) * enc_kpad(A, Kk) * 4;
+}
+
+int pack_encoder_mma(const float* W, int N, int A, int Kk, void* packed, cudaStream_t st) {
+    if (!encoder_mma_packed_bytes(N, A, Kk)) return SDR_ERR_UNSUPPORTED;
+    const int Mpad = mma_pad_m(N), K = enc_kpad(A, Kk);
+    const long long chunks = (long long)Mpad * K / 8;
+    pack_weight_mma_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(
+        W, static_cast<uint8_t*>(packed), N, Mpad, A * Kk, K, mma_tile_n(N));
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* stats,
+                       int B, int A, long long T, int N, int Kk, int L, cudaStream_t st) {
+    if (!encoder_mma_packed_bytes(N, A, Kk)) return SDR_ERR_UNSUPPORTED;
+    if (B <= 0 || T <= 0 || L <= 0 || !wav || !wpk || !enc) return SDR_ERR_BAD_ARGUMENT;
+    MmaArgs a;
+    a.x = wav; a.nin = NormIn{nullptr, nullptr, nullptr, nullptr, 1.0};
+    a.wpk = static_cast<const uint8_t*>(wpk); a.bias = nullptr; a.residual = nullptr; a.gate = nullptr;
+    a.gate_channels = 0; a.y = enc; a.stats_out = stats;
+    a.M = N; a.K = enc_kpad(A, Kk); a.L = L; a.epilogue = 0;
+    a.win_k = Kk; a.win_hop = Kk / 2; a.win_pad = Kk / 2; a.win_a = A; a.win_T = T;
+    a.tile_n = mma_tile_n(N);
+    a.n_tiles = mma_pad_m(N) / a.tile_n;
+    a.l_tiles = (L + kTileM - 1) / kTileM;
+    const long long tiles = (long long)B * a.l_tiles * a.n_tiles;
+    if (tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    a.num_tiles = (int)tiles;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
+    if (cudaFuncSetAttribute(pw_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
+        return SDR_ERR_CUDA;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    pw_mma_kernel<true><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

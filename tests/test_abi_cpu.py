@@ -19,7 +19,7 @@ def test_header_symbols_are_exported():
     hdr = open(os.path.join(REPO, "include", "sudormrf_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(sdr_[a-z_0-9]+)\s*\(", hdr))
-    assert len(declared) >= 21
+    assert len(declared) >= 24
     lib = _native.lib()
     for name in declared:
         assert hasattr(lib, name), name

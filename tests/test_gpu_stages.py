@@ -118,6 +118,11 @@ def test_merge(samples, C_, L, depth):
     (2, 48, 20, 26, "norm"),              # odd sizes, scalar path (L % 4 != 0)
     (2, 130, 33, 100, "res"),             # M, K not multiples of the tile
     (1, 7, 5, 2, "mask"),
+    (32, 32, 16, 3200, "plain_stats"),    # small-channel streaming kernel, two 16-channel output tiles
+    (32, 16, 32, 3200, "res"),            # ... with normalised + PReLU input and in-place skip
+    (3, 24, 8, 132, "norm"),              # ... M not a multiple of 16, ragged last quad chunk
+    (2, 64, 64, 64, "mask"),              # ... largest shape it takes
+    (2, 8, 4, 4, "plain_stats"),
 ])
 def test_pointwise(samples, M, K, L, mode):
     g = torch.Generator().manual_seed(2)
@@ -189,6 +194,35 @@ def test_encoder(B, A, T, N_, K, D):
     assert want.shape[-1] == L
     close(enc, want)
     check_stats(st, want)
+
+
+@pytest.mark.parametrize("B,A,T,N_,K,D", [
+    (2, 1, 32000, 512, 21, 5), (3, 1, 517, 48, 21, 3), (2, 1, 100, 32, 21, 5),
+    (2, 2, 333, 160, 11, 3), (1, 1, 7, 70, 21, 1), (1, 1, 3000, 64, 91, 4), (40, 1, 6400, 256, 21, 5),
+])
+def test_encoder_tensor_core(B, A, T, N_, K, D):
+    """Encoder on the tcgen05 kernel (window operand, bf16x3)."""
+    lib = N.lib()
+    g = torch.Generator().manual_seed(3)
+    cfg = O.Config(enc_kernel_size=K, upsampling_depth=D)
+    Tp = O.padded_length(cfg, T)
+    hop = K // 2
+    L = Tp // hop
+    wav = torch.randn(B, A, T, generator=g).to(DEV)
+    w = torch.randn(N_, A, K, generator=g).to(DEV)
+    nbytes = lib.sdr_encoder_mma_packed_bytes(N_, A, K)
+    assert nbytes > 0
+    wpk = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    N.check(lib.sdr_encoder_mma_pack(p(w), N_, A, K, p(wpk), stream()))
+    enc = torch.full((B, N_, L), float("nan"), device=DEV)
+    st = torch.zeros(B, 2, dtype=torch.float64, device=DEV)
+    N.check(lib.sdr_encoder_mma(p(wav), p(wpk), p(enc), p(st), B, A, T, N_, K, L, stream()))
+    xp = torch.zeros(B, A, Tp, device=DEV, dtype=torch.float64)
+    xp[..., :T] = wav
+    want = F.conv1d(xp, w.double(), None, stride=hop, padding=hop)
+    assert want.shape[-1] == L
+    close(enc, want, tol=5e-5)
+    check_stats(st, want.float(), rtol=3e-5)
 
 
 @pytest.mark.parametrize("B,SA,K,L,T,mc", [
