@@ -35,8 +35,9 @@ int launch_encoder_mma(const float*, const void*, float*, double*, int, int, lon
 static int pointwise(const float* x, const NormIn& nin, const float* W, const float* wpk, const float* bias,
                      const float* residual, const float* gate, int gate_channels, float* y, double* stats,
                      int samples, int M, int K, int L, int epilogue, cudaStream_t st) {
-    if (wpk) return launch_pointwise_mma(x, nin, wpk, bias, residual, gate, gate_channels, y, stats,
-                                         samples, M, K, L, epilogue, st);
+    if (wpk && (L % 4) == 0)       // the tensor-core kernel loads activations as float4
+        return launch_pointwise_mma(x, nin, wpk, bias, residual, gate, gate_channels, y, stats,
+                                    samples, M, K, L, epilogue, st);
     return launch_pointwise_ffma(x, nin, W, bias, residual, gate, gate_channels, y, stats,
                                  samples, M, K, L, epilogue, st);
 }

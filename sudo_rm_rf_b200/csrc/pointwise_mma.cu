@@ -37,7 +37,9 @@ constexpr int kBStageBytes = 2 * kBHalfMax;                  // 64 KB: hi + lo
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
-constexpr int kProdElems = kTileM * kBlockK / kProdThreads;  // 32 channels of one position per thread and k-block
+constexpr int kEpiChunk = 16;           // TMEM columns per epilogue step (register budget: 704 threads -> 88 regs)
+constexpr int kProdElems = kTileM * kBlockK / kProdThreads;  // 32 = 8 channels x 4 positions per thread and k-block
+static_assert(kProdWarps == 8 && kProdElems == 32, "one transform warp per 8-channel k-group, 4 positions per lane");
 
 struct MmaArgs {
     const float* x;
@@ -155,10 +157,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major,
-// N>>3 in [17,23), M>>4 in [24,29).
+// MN-major, SWIZZLE_128B descriptor (the A operand: positions contiguous).  Canonical layout in
+// 16 B units ((8,n),(8,k)):((1,LBO),(8,SBO)): a 128 B row holds 64 consecutive MN elements of one
+// k; 8 k-rows form a 1024 B atom (16 B chunk index XOR k%8); LBO = byte stride between 64-wide MN
+// blocks, SBO = byte stride between groups of 8 k.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+constexpr uint32_t kALbo = 1024;       // A tile: [8 k-groups][2 MN blocks][8 k rows][128 B]
+constexpr uint32_t kASbo = 2048;
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), A MN-major (bit 15),
+// B K-major, N>>3 in [17,23), M>>4 in [24,29).
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------
@@ -219,7 +236,7 @@ pw_mma_kernel(const MmaArgs a) {
     // warp-private tables (no CTA-level barrier in the steady state): per transform warp the
     // (scale, shift) of its 32 channels, double-buffered; per epilogue warp a copy of the tile's bias
     float2* s_ab = reinterpret_cast<float2*>(b_base + kBStages * kBStageBytes);   // [kProdWarps][2][32]
-    float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 2 * 32);    // [kEpiWarps][256]
+    float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 64);    // [kEpiWarps][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kEpiWarps * kMaxTileN);
     uint64_t* full_bar = bars;                       // [kAStages]  8 transform warps + the TMA thread (+tx bytes)
     uint64_t* empty_bar = full_bar + kAStages;       // [kAStages]  one tcgen05.commit
@@ -246,21 +263,25 @@ pw_mma_kernel(const MmaArgs a) {
 
     if (warp >= kProdWarp0) {
         // ===================== A-operand transform producers =====================
-        const int pt = tid - kProdWarp0 * 32;      // 0..kProdThreads-1
-        const int p = pt & 127;                    // tile row (position); lanes = consecutive positions
-        const int cg = pt >> 7;                    // channel group: kProdElems channels of the k-block
-        const uint32_t row_off = (uint32_t)(p >> 3) * 1024 + (uint32_t)(p & 7) * 128;
+        // Warp w owns the 8 channels of k-group w of every k-block; lane i owns positions 4i..4i+3.
+        // Per channel a thread does ONE float4 load (a warp reads a 512 B row segment), the folded
+        // normalisation (+PReLU), the bf16 hi/lo split, and two conflict-free 8-byte stores into the
+        // MN-major SWIZZLE_128B tile (row = channel, 64 positions per 128 B row).
+        const int pw = warp - kProdWarp0;          // k-group (8 channels) of this warp
+        const int p4 = lane * 4;                   // first of this lane's 4 positions in the tile
         const bool has_norm = a.nin.stats != nullptr;
         const bool has_act = a.nin.prelu != nullptr;
         const float slope = has_act ? __ldg(a.nin.prelu) : 1.f;
-        static_assert(kProdElems == 32, "lane e of a transform warp owns channel e of the warp's 32-channel group");
-        float2* const my_tab = s_ab + (warp - kProdWarp0) * 64;   // this warp's [2][32] (scale, shift) table
+        const bool slope_le1 = slope <= 1.f;
+        float2* const my_tab = s_ab + pw * 64;     // this warp's [2][8] (scale, shift) table (lane e < 8)
         const double inv_count = 1.0 / a.nin.count;
         const size_t Ls = (size_t)a.L;
+        // byte offset of (channel row e = 0, this lane's positions) inside an A half tile
+        const uint32_t lane_off = (uint32_t)pw * kASbo + (uint32_t)(lane >> 4) * kALbo + (uint32_t)(lane & 1) * 8;
+        const uint32_t lane_chunk = (uint32_t)((lane & 15) >> 1);
 
         struct Cur { int tile, kb; TileCoord tc; };
-        // everything a step needs from global memory, fetched one step ahead into registers
-        struct Pre { float v[kProdElems]; float g, b; double s0, s1; };
+        struct Pre { float4 v[8]; float g, b; double s0, s1; };
         auto advance = [&](Cur& c) {              // next (tile, k-block) of this CTA; tile >= num_tiles == end
             if (++c.kb == KB) {
                 c.kb = 0;
@@ -269,29 +290,33 @@ pw_mma_kernel(const MmaArgs a) {
             }
         };
         auto issue_loads = [&](Pre& d, const Cur& c) {
-            const int l = c.tc.l0 + p;
+            const int l = c.tc.l0 + p4;
             const bool live = c.tile < a.num_tiles;
             if constexpr (WINDOW) {                // encoder: strided analysis windows of the waveform
-                const long long t0 = (long long)a.win_hop * l - a.win_pad;
 #pragma unroll
-                for (int e = 0; e < kProdElems; ++e) {
-                    const int k = c.kb * kBlockK + cg * kProdElems + e;
+                for (int e = 0; e < 8; ++e) {
+                    const int k = c.kb * kBlockK + pw * 8 + e;
                     const int ch = k / a.win_k, j = k - ch * a.win_k;
-                    const long long t = t0 + j;
-                    d.v[e] = (live && l < a.L && ch < a.win_a && t >= 0 && t < a.win_T)
-                                 ? __ldg(a.x + ((size_t)c.tc.sample * a.win_a + ch) * a.win_T + t) : 0.f;
-                }
-            } else if (live && l < a.L) {   // (pointwise mode)
-                const float* xs = a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + cg * kProdElems) * Ls + l;
+                    float vv[4];
 #pragma unroll
-                for (int e = 0; e < kProdElems; ++e) { d.v[e] = __ldg(xs); xs += Ls; }
+                    for (int u = 0; u < 4; ++u) {
+                        const long long t = (long long)a.win_hop * (l + u) + j - a.win_pad;
+                        vv[u] = (live && l + u < a.L && ch < a.win_a && t >= 0 && t < a.win_T)
+                                    ? __ldg(a.x + ((size_t)c.tc.sample * a.win_a + ch) * a.win_T + t) : 0.f;
+                    }
+                    d.v[e] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                }
+            } else if (live && l < a.L) {          // L % 4 == 0: the quad is entirely inside the row
+                const float* xs = a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + pw * 8) * Ls + l;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { d.v[e] = ldg4(xs); xs += Ls; }
             } else {
 #pragma unroll
-                for (int e = 0; e < kProdElems; ++e) d.v[e] = 0.f;
+                for (int e = 0; e < 8; ++e) d.v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             d.g = 1.f; d.b = 0.f; d.s0 = 0.0; d.s1 = 1.0;
-            if (has_norm && live) {                // lane e: gamma/beta of channel e of this warp's group
-                const int k = c.kb * kBlockK + cg * kProdElems + lane;
+            if (has_norm && live) {                // lane e: gamma/beta of channel e of this warp's k-group
+                const int k = c.kb * kBlockK + pw * 8 + (lane & 7);
                 d.g = __ldg(a.nin.gamma + k);
                 d.b = __ldg(a.nin.beta + k);
                 if (c.kb == 0) {                   // new tile: its sample's (sum, sumsq)
@@ -300,14 +325,12 @@ pw_mma_kernel(const MmaArgs a) {
                 }
             }
         };
-        // L2 prefetch of a step's activation tile: one 128 B line per (warp, channel) -> lane e takes
-        // channel e of this warp's 32-channel group.  Issued two steps ahead so that the register
-        // loads one step ahead are L2 hits (HBM latency x 32 KB in flight per SM was the limiter).
+        // L2 prefetch two steps ahead: this warp's 8 channel rows x 512 B = 32 lines, one per lane
         auto prefetch_step = [&](const Cur& c) {
             if (!WINDOW && c.tile < a.num_tiles) {
-                const int l = c.tc.l0 + (p & ~31);
+                const int l = c.tc.l0 + (lane >> 3) * 32;
                 if (l < a.L)
-                    prefetch_l2(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + cg * kProdElems + lane) * Ls + l);
+                    prefetch_l2(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + pw * 8 + (lane & 7)) * Ls + l);
             }
         };
         uint32_t it = 0;
@@ -323,41 +346,42 @@ pw_mma_kernel(const MmaArgs a) {
                         double var = d.s1 * inv_count - mu * mu;
                         var = var < 0.0 ? 0.0 : var;
                         mean = (float)mu;
-                        rstd = (float)(1.0 / sqrt(var + (double)kGlnEps));
+                        rstd = rsqrtf((float)var + kGlnEps);
                     }
                     aa = d.g * rstd;
                     bb = d.b - mean * aa;
                 }
-                my_tab[(it & 1) * 32 + lane] = make_float2(aa, bb);
+                if (lane < 8) my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
             }
             __syncwarp();                          // table visible to the warp (reuse is ordered by the next __syncwarp)
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
             uint8_t* a_lo = a_hi + kAHalf;
-            const float4* tab = reinterpret_cast<const float4*>(my_tab + (it & 1) * 32);
+            const float2* tab = my_tab + (it & 1) * 8;
 #pragma unroll
-            for (int cc = 0; cc < kProdElems / 8; ++cc) {
-                uint32_t hi[4], lo[4];
+            for (int e = 0; e < 8; ++e) {
+                const float2 ab = tab[e];
+                float y[4] = {fmaf(d.v[e].x, ab.x, ab.y), fmaf(d.v[e].y, ab.x, ab.y),
+                              fmaf(d.v[e].z, ab.x, ab.y), fmaf(d.v[e].w, ab.x, ab.y)};
+                if (has_act) {                     // PReLU in 2 ops: max(y, s*y) for s <= 1, min otherwise
 #pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    const float4 ab = tab[cc * 4 + e2];                 // (a0, b0, a1, b1)
-                    float y0 = fmaf(d.v[cc * 8 + 2 * e2], ab.x, ab.y);
-                    float y1 = fmaf(d.v[cc * 8 + 2 * e2 + 1], ab.z, ab.w);
-                    if (has_act) {
-                        y0 = y0 >= 0.f ? y0 : y0 * slope;
-                        y1 = y1 >= 0.f ? y1 : y1 * slope;
+                    for (int u = 0; u < 4; ++u) {
+                        const float t = y[u] * slope;
+                        y[u] = slope_le1 ? fmaxf(y[u], t) : fminf(y[u], t);
                     }
-                    // hi = top 16 bits (truncation), lo = bf16(y - hi): y - hi is exact in fp32, so
-                    // |y - hi - lo| <= 2^-9 |y - hi| <= 2^-16 |y|
-                    const uint32_t b0 = __float_as_uint(y0) & 0xffff0000u, b1 = __float_as_uint(y1) & 0xffff0000u;
-                    hi[e2] = __byte_perm(b0, b1, 0x7632);
-                    const __nv_bfloat162 lw = __floats2bfloat162_rn(y0 - __uint_as_float(b0), y1 - __uint_as_float(b1));
-                    lo[e2] = *reinterpret_cast<const uint32_t*>(&lw);
                 }
-                const int c8 = cg * (kProdElems / 8) + cc;              // 16 B chunk index within the 128 B row
-                const uint32_t off = row_off + (uint32_t)((c8 ^ (p & 7)) << 4);
-                *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                // hi = top 16 bits (truncation), lo = bf16(y - hi): y - hi is exact in fp32, so
+                // |y - hi - lo| <= 2^-9 |y - hi| <= 2^-16 |y|
+                uint32_t hb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) hb[u] = __float_as_uint(y[u]) & 0xffff0000u;
+                const uint32_t h01 = __byte_perm(hb[0], hb[1], 0x7632), h23 = __byte_perm(hb[2], hb[3], 0x7632);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[0] - __uint_as_float(hb[0]), y[1] - __uint_as_float(hb[1]));
+                const __nv_bfloat162 l23 = __floats2bfloat162_rn(y[2] - __uint_as_float(hb[2]), y[3] - __uint_as_float(hb[3]));
+                const uint32_t off = lane_off + (uint32_t)e * 128 + ((lane_chunk ^ (uint32_t)e) << 4);
+                *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
+                                                                    *reinterpret_cast<const uint32_t*>(&l23));
             }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
@@ -427,8 +451,9 @@ pw_mma_kernel(const MmaArgs a) {
                     const uint32_t sb_lo = sb_hi + bhalf;
 #pragma unroll
                     for (int ks = 0; ks < kBlockK / 16; ++ks) {
-                        const uint64_t dah = umma_desc_sw128(sa_hi + ks * 32);
-                        const uint64_t dal = umma_desc_sw128(sa_lo + ks * 32);
+                        // A is MN-major: a K=16 step spans two 8-channel groups (2 * SBO bytes apart)
+                        const uint64_t dah = umma_desc_mn_sw128(sa_hi + ks * 2 * kASbo, kALbo, kASbo);
+                        const uint64_t dal = umma_desc_mn_sw128(sa_lo + ks * 2 * kASbo, kALbo, kASbo);
                         const uint64_t dbh = umma_desc_sw128(sb_hi + ks * 32);
                         const uint64_t dbl = umma_desc_sw128(sb_lo + ks * 32);
                         umma_bf16(d_tmem, dah, dbh, idesc, (kb | ks) != 0 ? 1u : 0u);
@@ -447,7 +472,7 @@ pw_mma_kernel(const MmaArgs a) {
         const bool gated = a.epilogue == 1;
         const bool do_stats = a.stats_out != nullptr;
         const size_t Ls = (size_t)a.L;
-        const int nchunks = a.tile_n / 32;
+        const int nchunks = a.tile_n / kEpiChunk;
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
             const int acc = ti & 1;
@@ -485,32 +510,32 @@ pw_mma_kernel(const MmaArgs a) {
             // 32-column chunks.  The extra operand does not depend on the accumulator, so its loads run
             // one chunk ahead (EA/EB ping-pong, first chunk issued before the accumulator is complete);
             // a chunk's extra loads are always issued before the stores of the chunk before it.
-            float EA[32], EB[32];
-            uint32_t R[32];
+            float EA[kEpiChunk], EB[kEpiChunk];
+            uint32_t R[kEpiChunk];
             const float* ep = extra;
             const bool full_tile = ncols == a.tile_n;          // no zero-padded output channels in this tile
-            auto issue_ex = [&](float (&E)[32], int c) {
-                if (ep != nullptr && c < nchunks && (full_tile || (c + 1) * 32 <= ncols)) {
+            auto issue_ex = [&](float (&E)[kEpiChunk], int c) {
+                if (ep != nullptr && c < nchunks && (full_tile || (c + 1) * kEpiChunk <= ncols)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { E[j] = *ep; ep += Ls; }
-                } else if (ep != nullptr && c * 32 < ncols) {       // partially padded chunk
+                    for (int j = 0; j < kEpiChunk; ++j) { E[j] = *ep; ep += Ls; }
+                } else if (ep != nullptr && c * kEpiChunk < ncols) {       // partially padded chunk
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { E[j] = (c * 32 + j < ncols) ? *ep : 0.f; ep += Ls; }
+                    for (int j = 0; j < kEpiChunk; ++j) { E[j] = (c * kEpiChunk + j < ncols) ? *ep : 0.f; ep += Ls; }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) E[j] = 0.f;
+                    for (int j = 0; j < kEpiChunk; ++j) E[j] = 0.f;
                 }
             };
             float* yp = a.y + out_row0;
-            auto process = [&](const float (&E)[32], int c) {
-                tmem_ld32(t_acc + (uint32_t)(c * 32), R);
+            auto process = [&](const float (&E)[kEpiChunk], int c) {
+                tmem_ld16(t_acc + (uint32_t)(c * kEpiChunk), R);
                 tmem_ld_wait();
-                const int jmax = ncols - c * 32;               // >= 32 for a full chunk
+                const int jmax = ncols - c * kEpiChunk;        // >= kEpiChunk for a full chunk
                 if (!valid || jmax <= 0) return;
-                const float4* b4 = reinterpret_cast<const float4*>(sb + c * 32);
-                if (jmax >= 32) {                              // fast path: no per-column predicate
+                const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiChunk);
+                if (jmax >= kEpiChunk) {                              // fast path: no per-column predicate
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
+                    for (int j4 = 0; j4 < kEpiChunk / 4; ++j4) {
                         const float4 bv = b4[j4];
                         const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
@@ -525,8 +550,8 @@ pw_mma_kernel(const MmaArgs a) {
                     }
                 } else {                                       // last, partially padded chunk of a padded tile
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float o = __uint_as_float(R[j]) + sb[c * 32 + j];
+                    for (int j = 0; j < kEpiChunk; ++j) {
+                        float o = __uint_as_float(R[j]) + sb[c * kEpiChunk + j];
                         o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
                         if (j < jmax) {
                             *yp = o;
@@ -593,15 +618,17 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
 }
 
 constexpr size_t kMmaSmemBytes = (size_t)kAStages * kAStageBytes + (size_t)kBStages * kBStageBytes +
-                                 kProdWarps * 2 * 32 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
+                                 kProdWarps * 64 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
                                  (2 * kAStages + 4 + 2) * sizeof(uint64_t);
+static_assert(kEpiChunk == 16, "tmem_ld16 is hard-wired in the epilogue");
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
                          const float* residual, const float* gate, int gate_channels,
                          float* y, double* stats_out, int samples, int M, int K, int L,
                          int epilogue, cudaStream_t st) {
-    if (!pointwise_mma_eligible(M, K)) return SDR_ERR_UNSUPPORTED;
+    if (!pointwise_mma_eligible(M, K) || (L % 4) != 0 || (reinterpret_cast<uintptr_t>(x) % 16) != 0)
+        return SDR_ERR_UNSUPPORTED;                      // float4 activation loads
     if (samples <= 0 || L <= 0 || !x || !wpk || !y) return SDR_ERR_BAD_ARGUMENT;
     if (epilogue == 1 && (!gate || gate_channels <= 0)) return SDR_ERR_BAD_ARGUMENT;
     if (epilogue == 1 && (gate_channels % mma_tile_n(M)) != 0) return SDR_ERR_UNSUPPORTED;

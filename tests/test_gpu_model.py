@@ -122,6 +122,19 @@ def test_properties_at_benchmark_size():
         assert max(O.parity_errors(y[7:8], ref)) < TOL
 
 
+def test_depth1_model_with_unaligned_frame_count():
+    """upsampling_depth=1 allows L % 4 != 0: big channel counts then run on the FFMA kernels."""
+    kw = dict(out_channels=128, in_channels=128, num_blocks=2, upsampling_depth=1,
+              enc_kernel_size=21, enc_num_basis=64, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=8)
+    m = build("improved", kw, sd)
+    x = torch.randn(2, 1, 1290, generator=torch.Generator().manual_seed(0))     # Tp = 1300 -> L = 130
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert max(O.parity_errors(y, O.forward(cfg, sd, x))) < 1e-4
+
+
 def test_host_entry_and_dtype_handling():
     kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
               enc_kernel_size=21, enc_num_basis=48, num_sources=2)

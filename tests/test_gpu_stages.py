@@ -291,10 +291,10 @@ def test_mixture_consistency(kind):
     (2, 1024, 256, 384, "mask"),          # mask_net
     (2, 128, 64, 200, "res"),             # single k-block, 128-wide tile, ragged last position tile
     (1, 384, 192, 100, "plain_stats"),    # tile_n = 128 x 3, 3 k-blocks, L < 128
-    (5, 256, 128, 130, "norm"),           # more tiles than... positions spill into a 2nd tile
+    (5, 256, 128, 132, "norm"),           # positions spill into a 2nd, ragged tile
     (40, 512, 512, 384, "plain_stats"),   # > 148 tiles: persistent CTAs loop, both TMEM stages reused
     (3, 42, 1024, 200, "plain"),          # decoder GEMM: 42 rows zero-padded to one 128-wide tile
-    (2, 300, 128, 333, "res"),            # 300 rows -> padded to 384 = 3 tiles of 128, last one partial
+    (2, 300, 128, 332, "res"),            # 300 rows -> padded to 384 = 3 tiles of 128, last one partial
     (2, 160, 64, 64, "plain_stats"),      # padded to 256: one 256-wide tile with 96 padding columns
 ])
 def test_pointwise_tensor_core(samples, M, K, L, mode):
@@ -349,6 +349,20 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
     assert max(e) < 5e-5, e
     if want_stats:
         check_stats(st, want.float(), rtol=3e-5)
+
+
+def test_pointwise_tensor_core_refuses_unaligned_length():
+    """float4 activation loads need L % 4 == 0; the forward uses the FFMA kernel for such lengths."""
+    lib = N.lib()
+    x = torch.zeros(1, 64, 130, device=DEV)
+    W = torch.zeros(128, 64, device=DEV)
+    wpk = torch.empty(lib.sdr_pointwise_mma_packed_bytes(128, 64), dtype=torch.uint8, device=DEV)
+    N.check(lib.sdr_pointwise_mma_pack(p(W), 128, 64, p(wpk), stream()))
+    y = torch.zeros(1, 128, 130, device=DEV)
+    nin = norm_in()
+    rc = lib.sdr_pointwise_mma(p(x), C.byref(nin), p(wpk), p(None), p(None), p(None), 0, p(y), p(None),
+                               1, 128, 64, 130, 0, stream())
+    assert rc == -5
 
 
 def test_pointwise_tensor_core_eligibility():
