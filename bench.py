@@ -103,7 +103,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -297,7 +297,12 @@ def run_b200(args, w, wl_name):
         value = total_mix / (dev_ms / 1e3)
         fwd_bytes = B * am["a_mix"] + 4 * n_params
         fwd_gbs = fwd_bytes / (dev_ms / args.steps / 1e3) / 1e9
-        cpu_rate, cpu_sec, cpu_done = cpu_forward_rate(w, 2, steps=64, warmup=1, budget_s=12.0)
+        if world == 1:      # the CPU leg is timed at N=1 only (torchrun pins OMP threads to 1 per rank)
+            cpu_rate, cpu_sec, cpu_done = cpu_forward_rate(w, 2, steps=64, warmup=1, budget_s=12.0)
+            cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"{cpu_done} forwards of batch 2 x {T} samples ({cpu_sec:.2f} s each), same model"}
+        else:
+            cpu_baseline = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -320,10 +325,7 @@ def run_b200(args, w, wl_name):
             "forward_hbm": {"algorithmic_bytes_per_step": fwd_bytes, "achieved": fwd_gbs, "peak": peak,
                             "unit": "GB/s", "frac": fwd_gbs / peak, "peak_source": peak_src,
                             "gflop_per_mixture": am["flops"] / 1e9},
-            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(),
-                             "kind": "port",
-                             "sample": f"{cpu_done} forwards of batch 2 x {T} samples "
-                                       f"({cpu_sec:.2f} s each), same model"},
+            "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -386,12 +388,18 @@ def time_dominant_kernel(w, B, stream, flush, dev):
     ms = sorted(s.elapsed_time(e) for s, e in evs)
     avg = sum(ms) / len(ms)
     peak, peak_src = load_peaks()
+    traffic = None      # dram__bytes_read+write per launch of this kernel at this shape, from the committed ncu capture
+    tpath = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if t.get("shape") == {"samples": samples, "M": M, "K": K, "L": L}:
+            traffic = t.get("dram_bytes_per_launch")
     bytes_per_launch = B * am["res_bytes"]
     achieved = bytes_per_launch / (avg / 1e3) / 1e9
     return {"kernel": "pointwise GEMM res_conv+skip (" + ("pw_mma_kernel, tcgen05 bf16x3" if wpk is not None else "pw_gemm_kernel, FFMA") + ")",
             "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg,
             "tflops_fp32_equivalent": B * am["res_flops"] / (avg / 1e3) / 1e12,
             "shape": {"samples": samples, "M": M, "K": K, "L": L}}
@@ -400,7 +408,7 @@ def time_dominant_kernel(w, B, stream, flush, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="improved_u16_512", choices=sorted(WORKLOADS))

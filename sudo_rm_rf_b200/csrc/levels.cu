@@ -252,8 +252,43 @@ __device__ __forceinline__ float norm_act(float x, const FoldedNorm& f, float sl
     return y;
 }
 
-constexpr int kDw8Threads = 256;
-constexpr int kDw8Items = 2;       // runs of 8 outputs per thread
+// tuning knobs, swept on the B200 (profiles/r01_level_kernel_sweep.md): 128 threads x 4 runs (2 for the
+// merge) beat 256x2 / 512x1 / 64x8; ld.global.nc.L1::no_allocate + st.global.cs made stride-2 levels ~25 % slower
+#ifndef SDR_DW_THREADS
+#define SDR_DW_THREADS 128
+#endif
+#ifndef SDR_DW_ITEMS
+#define SDR_DW_ITEMS 4
+#endif
+#ifndef SDR_MG_THREADS
+#define SDR_MG_THREADS 128
+#endif
+#ifndef SDR_MG_ITEMS
+#define SDR_MG_ITEMS 2
+#endif
+#ifndef SDR_STREAM_HINTS
+#define SDR_STREAM_HINTS 0
+#endif
+// streaming accesses: every byte of these kernels is touched once, so (optionally) keep it out of L1
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+#if SDR_STREAM_HINTS
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return ldg4(p);
+#endif
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+#if SDR_STREAM_HINTS
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+    *reinterpret_cast<float4*>(p) = v;
+#endif
+}
+constexpr int kDw8Threads = SDR_DW_THREADS;
+constexpr int kDw8Items = SDR_DW_ITEMS;       // runs of 8 outputs per thread
 
 // requires Lout % 8 == 0
 template <int STRIDE, bool ACT>
@@ -292,7 +327,7 @@ dw5_wide_kernel(const float* __restrict__ x, NormIn nin,
             if (STRIDE == 1) {
                 const float* xr = xs + (size_t)c * Lin + 8 * q;       // window v[0..11] = positions 8q-2 .. 8q+9
                 float v[12];
-                const float4 m0 = ldg4(xr), m1 = ldg4(xr + 4);
+                const float4 m0 = ld_stream4(xr), m1 = ld_stream4(xr + 4);
                 float2 l = make_float2(0.f, 0.f), r = make_float2(0.f, 0.f);
                 const bool hl = q > 0, hr = q < QR - 1;
                 if (hl) l = __ldg(reinterpret_cast<const float2*>(xr - 2));
@@ -315,7 +350,7 @@ dw5_wide_kernel(const float* __restrict__ x, NormIn nin,
             } else {
                 const float* xr = xs + (size_t)c * Lin + 16 * q;      // window v[0..18] = positions 16q-2 .. 16q+16
                 float v[19];
-                const float4 m0 = ldg4(xr), m1 = ldg4(xr + 4), m2 = ldg4(xr + 8), m3 = ldg4(xr + 12);
+                const float4 m0 = ld_stream4(xr), m1 = ld_stream4(xr + 4), m2 = ld_stream4(xr + 8), m3 = ld_stream4(xr + 12);
                 float2 l = make_float2(0.f, 0.f);
                 float r = 0.f;
                 const bool hl = q > 0, hr = 16 * q + 16 < Lin;
@@ -337,8 +372,8 @@ dw5_wide_kernel(const float* __restrict__ x, NormIn nin,
                 }
             }
             float* yr = ys + (size_t)c * Lout + 8 * q;
-            *reinterpret_cast<float4*>(yr) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(yr + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            st_stream4(yr, make_float4(o[0], o[1], o[2], o[3]));
+            st_stream4(yr + 4, make_float4(o[4], o[5], o[6], o[7]));
 #pragma unroll
             for (int i = 0; i < 8; ++i) { acc_s += o[i]; acc_q = fmaf(o[i], o[i], acc_q); }
         }
@@ -348,7 +383,8 @@ dw5_wide_kernel(const float* __restrict__ x, NormIn nin,
 
 // merge, 16 outputs per thread, coarse-to-fine: s_d[i] = z_d[i]*a_d + (b_d + s_{d+1}[i>>1])
 // requires depth >= 4 and L % 16 == 0
-constexpr int kMg16Threads = 256;
+constexpr int kMg16Threads = SDR_MG_THREADS;
+constexpr int kMg16Items = SDR_MG_ITEMS;
 __global__ void __launch_bounds__(kMg16Threads)
 merge_wide_kernel(MergeArgs a, float* __restrict__ m, double* __restrict__ stats_out,
                   int C, int L, int chunks_per_sample) {
@@ -360,18 +396,20 @@ merge_wide_kernel(MergeArgs a, float* __restrict__ m, double* __restrict__ stats
     __syncthreads();
     const int QR = L >> 4;
     const int items = C * QR;
-    const int item = chunk * kMg16Threads + threadIdx.x;
     float acc_s = 0.f, acc_q = 0.f;
-    if (item < items) {
+#pragma unroll
+    for (int iti = 0; iti < kMg16Items; ++iti) {
+      const int item = (chunk * kMg16Items + iti) * kMg16Threads + threadIdx.x;
+      if (item < items) {
         const int c = item / QR;
         const int q = item - c * QR;
         const size_t row = (size_t)sample * C + c;
         // issue every load of this run first
         const float* z0 = a.z[0] + row * L + 16 * q;
-        const float4 v00 = ldg4(z0), v01 = ldg4(z0 + 4), v02 = ldg4(z0 + 8), v03 = ldg4(z0 + 12);
+        const float4 v00 = ld_stream4(z0), v01 = ld_stream4(z0 + 4), v02 = ld_stream4(z0 + 8), v03 = ld_stream4(z0 + 12);
         const float* z1 = a.z[1] + row * (L >> 1) + 8 * q;
-        const float4 v10 = ldg4(z1), v11 = ldg4(z1 + 4);
-        const float4 v2 = ldg4(a.z[2] + row * (L >> 2) + 4 * q);
+        const float4 v10 = ld_stream4(z1), v11 = ld_stream4(z1 + 4);
+        const float4 v2 = ld_stream4(a.z[2] + row * (L >> 2) + 4 * q);
         const float2 v3 = __ldg(reinterpret_cast<const float2*>(a.z[3] + row * (L >> 3) + 2 * q));
         float base = 0.f;                      // levels >= 4 are constant over the run
         for (int d = 4; d < a.depth; ++d) {
@@ -398,9 +436,10 @@ merge_wide_kernel(MergeArgs a, float* __restrict__ m, double* __restrict__ stats
         float* mr = m + row * L + 16 * q;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(mr + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            st_stream4(mr + 4 * i, make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
 #pragma unroll
         for (int i = 0; i < 16; ++i) { acc_s += o[i]; acc_q = fmaf(o[i], o[i], acc_q); }
+      }
     }
     block_stats_atomic(acc_s, acc_q, stats_out, sample, s_red);
 }
@@ -461,7 +500,8 @@ int launch_merge(const float* const* z, const NormIn* nins, int depth, float* m,
     const bool vec = aligned && (L % 4 == 0);
     if (vec && depth >= 4 && (L % 16 == 0)) {
         const long long items = (long long)C * (L / 16);
-        const int chunks = (int)((items + kMg16Threads - 1) / kMg16Threads);
+        const int per_cta = kMg16Threads * kMg16Items;
+        const int chunks = (int)((items + per_cta - 1) / per_cta);
         const long long grid = (long long)chunks * samples;
         if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
         merge_wide_kernel<<<(unsigned)grid, kMg16Threads, 0, st>>>(a, m, stats_out, C, L, chunks);
