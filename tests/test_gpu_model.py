@@ -144,9 +144,21 @@ def test_host_entry_and_dtype_handling():
     x = torch.randn(3, 1, 4001, generator=torch.Generator().manual_seed(0))
     ref = O.forward(cfg, sd, x)
     hx = x.pin_memory()
-    hy = m.forward_host(hx)
+    hy = m.forward_host(hx)                  # 1st call: eager
     torch.cuda.synchronize()
     assert max(O.parity_errors(hy, ref)) < 1e-4
+    # 2nd call captures a CUDA graph of (H2D, forward, D2H); later calls replay it with new buffer contents
+    for seed in (11, 12, 13):
+        xn = torch.randn(3, 1, 4001, generator=torch.Generator().manual_seed(seed))
+        hx.copy_(xn)
+        m.forward_host(hx, hy)
+        torch.cuda.synchronize()
+        assert max(O.parity_errors(hy, O.forward(cfg, sd, xn))) < 1e-4
+    hx.copy_(x)
+    # pageable buffers take the eager path
+    hp = m.forward_host(x.clone(), torch.empty(3, 2, 4001))
+    torch.cuda.synchronize()
+    assert max(O.parity_errors(hp, ref)) < 1e-4
     with torch.no_grad():
         y64 = m(x.double().to(DEV))          # any float dtype is cast to fp32 (reference :312)
         y16 = m(x.half().to(DEV))
@@ -160,6 +172,9 @@ def test_host_entry_and_dtype_handling():
     sd2 = dict(sd)
     sd2["bottleneck.bias"] = sd["bottleneck.bias"] + 0.5
     assert max(O.parity_errors(y2, O.forward(cfg, sd2, x))) < 1e-4
+    m.forward_host(hx, hy)                   # ... and invalidate the captured host graph
+    torch.cuda.synchronize()
+    assert max(O.parity_errors(hy, O.forward(cfg, sd2, x))) < 1e-4
 
 
 def test_training_mode_with_grad_raises_and_eval_runs():
