@@ -223,3 +223,37 @@ def test_data_parallel_wrapper_single_device():
     with torch.no_grad():
         y = m(x.cuda())
     assert max(O.parity_errors(y, O.forward(cfg, sd, x))) < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_two_devices():
+    """nn.DataParallel over 2 GPUs: one host thread per device calls forward on a replica whose
+    parameters are freshly broadcast tensors (run_improved_sudormrf.py:118)."""
+    kw = dict(out_channels=128, in_channels=256, num_blocks=2, upsampling_depth=4,
+              enc_kernel_size=21, enc_num_basis=128, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=4)
+    m = torch.nn.DataParallel(build("improved", kw, sd), device_ids=[0, 1]).eval()
+    x = torch.randn(6, 1, 3000, generator=torch.Generator().manual_seed(0))
+    ref = O.forward(cfg, sd, x)
+    with torch.no_grad():
+        for _ in range(3):                      # replicas are rebuilt on every call
+            y = m(x.cuda(0))
+            assert y.device.index == 0 and max(O.parity_errors(y, ref)) < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_model_on_second_device():
+    kw = dict(out_channels=128, in_channels=256, num_blocks=1, upsampling_depth=3,
+              enc_kernel_size=21, enc_num_basis=128, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=6)
+    m = P.SuDORMRF(**kw)
+    m.load_state_dict(sd)
+    m = m.to("cuda:1").eval()
+    x = torch.randn(2, 1, 2000, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        y = m(x.to("cuda:1"))                   # current device stays cuda:0
+    assert y.device.index == 1 and max(O.parity_errors(y, O.forward(cfg, sd, x))) < 1e-4
+    with pytest.raises(RuntimeError):
+        m(x.to("cuda:0"))                       # parameters and input on different devices
