@@ -16,7 +16,6 @@ ap.add_argument("--workload", default="improved_u16_512")
 ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--only", default="")
-ap.add_argument("--debug", action="store_true")
 a = ap.parse_args()
 w = bench.WORKLOADS[a.workload]
 kw = w["kw"]
