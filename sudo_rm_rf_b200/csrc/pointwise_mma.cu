@@ -210,9 +210,14 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
     return t;
 }
 
-// WINDOW = true: encoder mode (strided waveform windows as the A operand), a separate instantiation so
-// the pointwise kernel's register allocation is unaffected.
-template <bool WINDOW>
+// Compile-time specialisation keeps the hot loops small: the kernel image was 64 KB (ping-pong-unrolled
+// producer + 8 specialised copies of the store loop) against a 32 KB L1.5 instruction cache, and the
+// per-chunk timeline showed the epilogue warps at IPC ~0.1 (instruction fetch stalls).
+//   WINDOW: encoder mode (strided waveform windows as the A operand)
+//   ACT:    PReLU in the operand transform
+//   MODE:   epilogue 0 = bias only, 1 = + residual (may alias y), 2 = ReLU * gate
+//   STATS:  accumulate (sum, sumsq) of the output
+template <bool WINDOW, bool ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 pw_mma_kernel(const MmaArgs a) {
     // Exactly the 227 KB an sm_100 CTA can own: 3 x 32 KB A stages + 2 x 64 KB B stages + 2.7 KB of
@@ -254,11 +259,12 @@ pw_mma_kernel(const MmaArgs a) {
         // Per channel a thread does ONE float4 load (a warp reads a 512 B row segment), the folded
         // normalisation (+PReLU), the bf16 hi/lo split, and two conflict-free 8-byte stores into the
         // MN-major SWIZZLE_128B tile (row = channel, 64 positions per 128 B row).
+        // Rolling prefetch: as soon as channel e of the current step is consumed its register is refilled
+        // with channel e of the NEXT step, so loads stay one k-block ahead with a single copy of the code.
         const int pw = warp - kProdWarp0;          // k-group (8 channels) of this warp
         const int p4 = lane * 4;                   // first of this lane's 4 positions in the tile
         const bool has_norm = a.nin.stats != nullptr;
-        const bool has_act = a.nin.prelu != nullptr;
-        const float slope = has_act ? __ldg(a.nin.prelu) : 1.f;
+        const float slope = ACT ? __ldg(a.nin.prelu) : 1.f;
         const bool slope_le1 = slope <= 1.f;
         float2* const my_tab = s_ab + pw * 64;     // this warp's [2][8] (scale, shift) table (lane e < 8)
         const double inv_count = 1.0 / a.nin.count;
@@ -268,7 +274,6 @@ pw_mma_kernel(const MmaArgs a) {
         const uint32_t lane_chunk = (uint32_t)((lane & 15) >> 1);
 
         struct Cur { int tile, kb; TileCoord tc; };
-        struct Pre { float4 v[8]; float g, b; double s0, s1; };
         auto advance = [&](Cur& c) {              // next (tile, k-block) of this CTA; tile >= num_tiles == end
             if (++c.kb == KB) {
                 c.kb = 0;
@@ -276,41 +281,38 @@ pw_mma_kernel(const MmaArgs a) {
                 if (c.tile < a.num_tiles) c.tc = decode_tile(a, c.tile);
             }
         };
-        auto issue_loads = [&](Pre& d, const Cur& c) {
+        // one channel row (4 positions) of step c
+        auto load_row = [&](const Cur& c, int e) -> float4 {
             const int l = c.tc.l0 + p4;
-            const bool live = c.tile < a.num_tiles;
+            if (c.tile >= a.num_tiles || l >= a.L) return make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (WINDOW) {                // encoder: strided analysis windows of the waveform
+                const int k = c.kb * kBlockK + pw * 8 + e;
+                const int ch = k / a.win_k, j = k - ch * a.win_k;
+                float vv[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int k = c.kb * kBlockK + pw * 8 + e;
-                    const int ch = k / a.win_k, j = k - ch * a.win_k;
-                    float vv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const long long t = (long long)a.win_hop * (l + u) + j - a.win_pad;
-                        vv[u] = (live && l + u < a.L && ch < a.win_a && t >= 0 && t < a.win_T)
-                                    ? __ldg(a.x + ((size_t)c.tc.sample * a.win_a + ch) * a.win_T + t) : 0.f;
-                    }
-                    d.v[e] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                for (int u = 0; u < 4; ++u) {
+                    const long long t = (long long)a.win_hop * (l + u) + j - a.win_pad;
+                    vv[u] = (l + u < a.L && ch < a.win_a && t >= 0 && t < a.win_T)
+                                ? __ldg(a.x + ((size_t)c.tc.sample * a.win_a + ch) * a.win_T + t) : 0.f;
                 }
-            } else if (live && l < a.L) {          // L % 4 == 0: the quad is entirely inside the row
-                const float* xs = a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + pw * 8) * Ls + l;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { d.v[e] = ldg4(xs); xs += Ls; }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) d.v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                return make_float4(vv[0], vv[1], vv[2], vv[3]);
+            } else {                               // L % 4 == 0: the quad is entirely inside the row
+                return ldg4(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + pw * 8 + e) * Ls + l);
             }
-            d.g = 1.f; d.b = 0.f; d.s0 = 0.0; d.s1 = 1.0;
-            if (has_norm && live) {                // lane e: gamma/beta of channel e of this warp's k-group
+        };
+        struct Aux { float g, b; double s0, s1; };
+        auto load_aux = [&](const Cur& c) -> Aux {   // lane e: gamma/beta of channel e of this warp's k-group
+            Aux x{1.f, 0.f, 0.0, 1.0};
+            if (has_norm && c.tile < a.num_tiles) {
                 const int k = c.kb * kBlockK + pw * 8 + (lane & 7);
-                d.g = __ldg(a.nin.gamma + k);
-                d.b = __ldg(a.nin.beta + k);
+                x.g = __ldg(a.nin.gamma + k);
+                x.b = __ldg(a.nin.beta + k);
                 if (c.kb == 0) {                   // new tile: its sample's (sum, sumsq)
-                    d.s0 = a.nin.stats[2 * (size_t)c.tc.sample];
-                    d.s1 = a.nin.stats[2 * (size_t)c.tc.sample + 1];
+                    x.s0 = a.nin.stats[2 * (size_t)c.tc.sample];
+                    x.s1 = a.nin.stats[2 * (size_t)c.tc.sample + 1];
                 }
             }
+            return x;
         };
         // L2 prefetch two steps ahead: this warp's 8 channel rows x 512 B = 32 lines, one per lane
         auto prefetch_step = [&](const Cur& c) {
@@ -320,84 +322,78 @@ pw_mma_kernel(const MmaArgs a) {
                     prefetch_l2(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + pw * 8 + (lane & 7)) * Ls + l);
             }
         };
-        uint32_t it = 0;
-        float mean = 0.f, rstd = 1.f;              // of the current tile's sample
-        auto process = [&](const Pre& d, const Cur& c) {
-            const int stage = it % kAStages;
-            const uint32_t phase = (it / kAStages) & 1;
-            {                                      // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
-                float aa = 1.f, bb = 0.f;
-                if (has_norm) {
-                    if (c.kb == 0) {
-                        const double mu = d.s0 * inv_count;
-                        double var = d.s1 * inv_count - mu * mu;
-                        var = var < 0.0 ? 0.0 : var;
-                        mean = (float)mu;
-                        rstd = rsqrtf((float)var + kGlnEps);
-                    }
-                    aa = d.g * rstd;
-                    bb = d.b - mean * aa;
-                }
-                if (lane < 8) my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
-            }
-            __syncwarp();                          // table visible to the warp (reuse is ordered by the next __syncwarp)
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
-            uint8_t* a_lo = a_hi + kAHalf;
-            const float2* tab = my_tab + (it & 1) * 8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float2 ab = tab[e];
-                float y[4] = {fmaf(d.v[e].x, ab.x, ab.y), fmaf(d.v[e].y, ab.x, ab.y),
-                              fmaf(d.v[e].z, ab.x, ab.y), fmaf(d.v[e].w, ab.x, ab.y)};
-                if (has_act) {                     // PReLU in 2 ops: max(y, s*y) for s <= 1, min otherwise
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float t = y[u] * slope;
-                        y[u] = slope_le1 ? fmaxf(y[u], t) : fminf(y[u], t);
-                    }
-                }
-                // hi = top 16 bits (truncation), lo = bf16(y - hi): y - hi is exact in fp32, so
-                // |y - hi - lo| <= 2^-9 |y - hi| <= 2^-16 |y|
-                uint32_t hb[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) hb[u] = __float_as_uint(y[u]) & 0xffff0000u;
-                const uint32_t h01 = __byte_perm(hb[0], hb[1], 0x7632), h23 = __byte_perm(hb[2], hb[3], 0x7632);
-                const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[0] - __uint_as_float(hb[0]), y[1] - __uint_as_float(hb[1]));
-                const __nv_bfloat162 l23 = __floats2bfloat162_rn(y[2] - __uint_as_float(hb[2]), y[3] - __uint_as_float(hb[3]));
-                const uint32_t off = lane_off + (uint32_t)e * 128 + ((lane_chunk ^ (uint32_t)e) << 4);
-                *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
-                *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
-                                                                    *reinterpret_cast<const uint32_t*>(&l23));
-            }
-            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
-            ++it;
-        };
 
-        Cur c0;
-        c0.tile = blockIdx.x; c0.kb = 0;
-        if (c0.tile < a.num_tiles) {
-            c0.tc = decode_tile(a, c0.tile);
-            // ping-pong register prefetch: the loads of step i+1 are in flight while step i is transformed
-            Pre pa, pb;
-            Cur c1 = c0, cp;
-            issue_loads(pa, c0);
-            advance(c1);
-            cp = c1;
-            prefetch_step(cp);
-            while (true) {
-                advance(cp); prefetch_step(cp);          // cp = two steps ahead of the step being processed
-                issue_loads(pb, c1);
-                process(pa, c0);
-                if (c1.tile >= a.num_tiles) break;
-                c0 = c1; advance(c0);
-                advance(cp); prefetch_step(cp);
-                issue_loads(pa, c0);
-                process(pb, c1);
-                if (c0.tile >= a.num_tiles) break;
-                c1 = c0; advance(c1);
+        Cur c;
+        c.tile = blockIdx.x; c.kb = 0;
+        if (c.tile < a.num_tiles) {
+            c.tc = decode_tile(a, c.tile);
+            float4 v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = load_row(c, e);
+            Aux aux = load_aux(c);
+            Cur cp = c;
+            advance(cp); prefetch_step(cp);
+            uint32_t it = 0;
+            float mean = 0.f, rstd = 1.f;          // of the current tile's sample
+#pragma unroll 1
+            while (c.tile < a.num_tiles) {
+                Cur n = c;
+                advance(n);                        // next step (n.tile >= num_tiles: none)
+                advance(cp); prefetch_step(cp);    // two steps ahead
+                const int stage = it % kAStages;
+                const uint32_t phase = (it / kAStages) & 1;
+                {                                  // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
+                    float aa = 1.f, bb = 0.f;
+                    if (has_norm) {
+                        if (c.kb == 0) {
+                            const double mu = aux.s0 * inv_count;
+                            double var = aux.s1 * inv_count - mu * mu;
+                            var = var < 0.0 ? 0.0 : var;
+                            mean = (float)mu;
+                            rstd = rsqrtf((float)var + kGlnEps);
+                        }
+                        aa = aux.g * rstd;
+                        bb = aux.b - mean * aa;
+                    }
+                    if (lane < 8) my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
+                    aux = load_aux(n);
+                }
+                __syncwarp();                      // table visible to the warp (reuse is ordered by the next __syncwarp)
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
+                uint8_t* a_lo = a_hi + kAHalf;
+                const float2* tab = my_tab + (it & 1) * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float2 ab = tab[e];
+                    float y[4] = {fmaf(v[e].x, ab.x, ab.y), fmaf(v[e].y, ab.x, ab.y),
+                                  fmaf(v[e].z, ab.x, ab.y), fmaf(v[e].w, ab.x, ab.y)};
+                    v[e] = load_row(n, e);         // refill: channel e of the next step
+                    if (ACT) {                     // PReLU in 2 ops: max(y, s*y) for s <= 1, min otherwise
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float t = y[u] * slope;
+                            y[u] = slope_le1 ? fmaxf(y[u], t) : fminf(y[u], t);
+                        }
+                    }
+                    // hi = top 16 bits (truncation), lo = bf16(y - hi): y - hi is exact in fp32, so
+                    // |y - hi - lo| <= 2^-9 |y - hi| <= 2^-16 |y|
+                    uint32_t hb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) hb[u] = __float_as_uint(y[u]) & 0xffff0000u;
+                    const uint32_t h01 = __byte_perm(hb[0], hb[1], 0x7632), h23 = __byte_perm(hb[2], hb[3], 0x7632);
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[0] - __uint_as_float(hb[0]), y[1] - __uint_as_float(hb[1]));
+                    const __nv_bfloat162 l23 = __floats2bfloat162_rn(y[2] - __uint_as_float(hb[2]), y[3] - __uint_as_float(hb[3]));
+                    const uint32_t off = lane_off + (uint32_t)e * 128 + ((lane_chunk ^ (uint32_t)e) << 4);
+                    *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
+                                                                        *reinterpret_cast<const uint32_t*>(&l23));
+                }
+                fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                ++it;
+                c = n;
             }
         }
     } else if (warp == kTmaWarp) {
@@ -456,11 +452,10 @@ pw_mma_kernel(const MmaArgs a) {
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int q = warp;                 // TMEM lane quarter of this warp
-        const bool gated = a.epilogue == 1;
-        const bool do_stats = a.stats_out != nullptr;
         const size_t Ls = (size_t)a.L;
         const int nchunks = a.tile_n / kEpiChunk;
         uint32_t ti = 0;
+#pragma unroll 1
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
@@ -474,53 +469,46 @@ pw_mma_kernel(const MmaArgs a) {
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
             const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0) * Ls + l;       // (m = n0, l)
-            // residual (may alias y: in-place skip connection) or gate operand of this tile
-            const float* extra = nullptr;
-            if (valid) {
-                if (gated) extra = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
-                else if (a.residual) extra = a.residual + out_row0;
-            }
+            // MODE 1: residual (may alias y: in-place skip connection); MODE 2: gate operand of this tile
+            const float* ep = nullptr;
+            if (MODE == 1) ep = a.residual + out_row0;
+            if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
             float st_s = 0.f, st_q = 0.f;
-            // pull this tile's residual / gate rows into L2 while the main loop runs: lane j of warp q
-            // takes the 128 B line (positions 32q..32q+31) of rows j, j+32, ...
-            if (gated || a.residual) {
+            if (MODE != 0) {               // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
                 if (lq < a.L) {
-                    const float* e0 = gated
-                        ? a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + lq
-                        : a.residual + ((size_t)tc.sample * a.M + tc.n0) * Ls + lq;
+                    const float* e0 = ep - lane;               // position lq of row 0
                     for (int j = lane; j < ncols; j += 32) prefetch_l2(e0 + (size_t)j * Ls);
                 }
             }
-
-            // 32-column chunks.  The extra operand does not depend on the accumulator, so its loads run
-            // one chunk ahead (EA/EB ping-pong, first chunk issued before the accumulator is complete);
-            // a chunk's extra loads are always issued before the stores of the chunk before it.
-            float EA[kEpiChunk], EB[kEpiChunk];
+            // Extra operand (MODE 1 residual / MODE 2 gate): it does not depend on the accumulator, so the 16
+            // loads of a chunk are issued as one burst a full chunk ahead (EA/EB ping-pong; the first burst before
+            // the accumulator is complete).  They may alias y (in-place skip), so a chunk's loads are always
+            // issued before the stores of the chunk before it, never interleaved after them.  (Rolling
+            // per-column refills, one or two chunks deep, measured 10 % slower.)
+            float EA[MODE != 0 ? kEpiChunk : 1], EB[MODE != 0 ? kEpiChunk : 1];
             uint32_t R[kEpiChunk];
-            const float* ep = extra;
-            const bool full_tile = ncols == a.tile_n;          // no zero-padded output channels in this tile
-            auto issue_ex = [&](float (&E)[kEpiChunk], int c) {
-                if (ep != nullptr && c < nchunks && (full_tile || (c + 1) * kEpiChunk <= ncols)) {
+            const float* epn = ep;
+            auto issue_ex = [&](float (&E)[MODE != 0 ? kEpiChunk : 1], int c) {
+                if constexpr (MODE != 0) {
+                    if (valid && c < nchunks && (c + 1) * kEpiChunk <= ncols) {
 #pragma unroll
-                    for (int j = 0; j < kEpiChunk; ++j) { E[j] = *ep; ep += Ls; }
-                } else if (ep != nullptr && c * kEpiChunk < ncols) {       // partially padded chunk
-#pragma unroll
-                    for (int j = 0; j < kEpiChunk; ++j) { E[j] = (c * kEpiChunk + j < ncols) ? *ep : 0.f; ep += Ls; }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kEpiChunk; ++j) E[j] = 0.f;
+                        for (int j = 0; j < kEpiChunk; ++j) { E[j] = *epn; epn += Ls; }
+                    } else {
+                        epn += (size_t)kEpiChunk * Ls;         // partial / padded chunk: its slow path loads directly
+                    }
                 }
             };
             float* yp = a.y + out_row0;
-            auto process = [&](const float (&E)[kEpiChunk], int c) {
+            auto do_chunk = [&](const float (&E)[MODE != 0 ? kEpiChunk : 1], int c) {
+                if (c >= nchunks) return;
                 tmem_ld16(t_acc + (uint32_t)(c * kEpiChunk), R);
                 tmem_ld_wait();
                 const int jmax = ncols - c * kEpiChunk;        // >= kEpiChunk for a full chunk
                 if (!valid || jmax <= 0) return;
                 const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiChunk);
-                if (jmax >= kEpiChunk) {                              // fast path: no per-column predicate
+                if (jmax >= kEpiChunk) {                       // full chunk: no per-column predicate
 #pragma unroll
                     for (int j4 = 0; j4 < kEpiChunk / 4; ++j4) {
                         const float4 bv = b4[j4];
@@ -529,37 +517,42 @@ pw_mma_kernel(const MmaArgs a) {
                         for (int u = 0; u < 4; ++u) {
                             const int j = j4 * 4 + u;
                             float o = __uint_as_float(R[j]) + bb[u];
-                            o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
+                            if (MODE == 1) o += E[MODE != 0 ? j : 0];
+                            if (MODE == 2) o = fmaxf(o, 0.f) * E[MODE != 0 ? j : 0];
                             *yp = o;
                             yp += Ls;
-                            if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
+                            if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
                         }
                     }
                 } else {                                       // last, partially padded chunk of a padded tile
+#pragma unroll 1
+                    for (int j = 0; j < jmax; ++j) {
+                        float o = __uint_as_float(R[0]);
 #pragma unroll
-                    for (int j = 0; j < kEpiChunk; ++j) {
-                        float o = __uint_as_float(R[j]) + sb[c * kEpiChunk + j];
-                        o = gated ? fmaxf(o, 0.f) * E[j] : o + E[j];
-                        if (j < jmax) {
-                            *yp = o;
-                            if (do_stats) { st_s += o; st_q = fmaf(o, o, st_q); }
-                        }
-                        yp += Ls;
+                        for (int u = 1; u < kEpiChunk; ++u) if (u == j) o = __uint_as_float(R[u]);
+                        o += sb[c * kEpiChunk + j];
+                        float ev = 0.f;
+                        if (MODE != 0) ev = ep[(size_t)(c * kEpiChunk + j) * Ls];
+                        if (MODE == 1) o += ev;
+                        if (MODE == 2) o = fmaxf(o, 0.f) * ev;
+                        yp[(size_t)j * Ls] = o;
+                        if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
                     }
                 }
             };
             issue_ex(EA, 0);
             mbar_wait(&tfull_bar[acc], aphase);
             tc_fence_after();
+#pragma unroll 1
             for (int c = 0; c < nchunks; c += 2) {
                 issue_ex(EB, c + 1);
-                process(EA, c);
+                do_chunk(EA, c);
                 issue_ex(EA, c + 2);
-                if (c + 1 < nchunks) process(EB, c + 1);
+                do_chunk(EB, c + 1);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
-            if (do_stats) {
+            if (STATS) {
                 st_s = warp_sum(st_s);
                 st_q = warp_sum(st_q);
                 if (lane == 0) {
@@ -635,10 +628,24 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    if (cudaFuncSetAttribute(pw_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
-        return SDR_ERR_CUDA;
-    pw_mma_kernel<false><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
-    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+    const bool act = nin.prelu != nullptr;
+    const int mode = epilogue == 1 ? 2 : (residual ? 1 : 0);
+    const bool stats = stats_out != nullptr;
+#define SDR_MMA_CASE(A, MD, ST)                                                                                   \
+    if (act == A && mode == MD && stats == ST) {                                                                  \
+        if (cudaFuncSetAttribute(pw_mma_kernel<false, A, MD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 (int)kMmaSmemBytes) != cudaSuccess) return SDR_ERR_CUDA;                         \
+        pw_mma_kernel<false, A, MD, ST><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);                             \
+        return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;                                         \
+    }
+    SDR_MMA_CASE(false, 0, false) SDR_MMA_CASE(false, 0, true)
+    SDR_MMA_CASE(true, 0, false)  SDR_MMA_CASE(true, 0, true)
+    SDR_MMA_CASE(false, 1, false) SDR_MMA_CASE(false, 1, true)
+    SDR_MMA_CASE(true, 1, false)  SDR_MMA_CASE(true, 1, true)
+    SDR_MMA_CASE(false, 2, false) SDR_MMA_CASE(false, 2, true)
+    SDR_MMA_CASE(true, 2, false)  SDR_MMA_CASE(true, 2, true)
+#undef SDR_MMA_CASE
+    return SDR_ERR_UNSUPPORTED;
 }
 
 // ---- encoder on the same kernel (window mode) ----
@@ -677,10 +684,16 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
-    if (cudaFuncSetAttribute(pw_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
-        return SDR_ERR_CUDA;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    pw_mma_kernel<true><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+    if (stats) {
+        if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
+            return SDR_ERR_CUDA;
+        pw_mma_kernel<true, false, 0, true><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+    } else {
+        if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
+            return SDR_ERR_CUDA;
+        pw_mma_kernel<true, false, 0, false><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+    }
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
