@@ -19,6 +19,8 @@
 //
 // Replaces (reference file:line): bottleneck improved_sudormrf.py:256-259,292;
 // proj_1x1.conv :174,205; res_conv(+skip) :196,220; mask_net :268-269,295-298.
+#include <cstring>
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -38,6 +40,11 @@ constexpr int kBStageBytes = 2 * kBHalfMax;                  // 64 KB: hi + lo
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
+#ifndef SDR_MMA_BULK
+#define SDR_MMA_BULK 1                  // 1: the in-place skip connection (mode 3) leaves through staging tiles + TMA reduce-add
+#endif
+constexpr int kStgBufs = 3;             // ring of [16 channels][128 positions] fp32 staging tiles (one TMA box each)
+constexpr int kStgFloats = 16 * 128;
 constexpr int kEpiChunk = 16;           // TMEM columns per epilogue step (x16 / x32 / x64 measured the same; 16 keeps registers low)
 constexpr int kProdElems = kTileM * kBlockK / kProdThreads;  // 32 = 8 channels x 4 positions per thread and k-block
 static_assert(kProdWarps == 8 && kProdElems == 32, "one transform warp per 8-channel k-group, 4 positions per lane");
@@ -99,6 +106,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// shared -> global tensor (TMA) reduce-add of one [16 channels][128 positions] box into the [samples][M][L]
+// output (fp32 add performed in L2); rows / positions outside the tensor are clipped by the hardware.  The issuing thread tracks completion
+// with bulk groups.  (1-D bulk copies of 128 B rows measured ~17 ns per copy: request-rate bound.)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -215,13 +234,14 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
 // per-chunk timeline showed the epilogue warps at IPC ~0.1 (instruction fetch stalls).
 //   WINDOW: encoder mode (strided waveform windows as the A operand)
 //   ACT:    PReLU in the operand transform
-//   MODE:   epilogue 0 = bias only, 1 = + residual (may alias y), 2 = ReLU * gate
+//   MODE:   epilogue 0 = bias only, 1 = + residual (may alias y), 2 = ReLU * gate,
+//           3 = in-place skip connection (y == residual): y += acc + bias as a bulk reduce-add in L2
 //   STATS:  accumulate (sum, sumsq) of the output
 template <bool WINDOW, bool ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(kMmaThreads, 1)
-pw_mma_kernel(const MmaArgs a) {
-    // Exactly the 227 KB an sm_100 CTA can own: 3 x 32 KB A stages + 2 x 64 KB B stages + 2.7 KB of
-    // tables and barriers.  SWIZZLE_128B needs the stage bases 1024 B aligned.
+pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
+    // 2 x 32 KB A stages + 2 x 64 KB B stages + 8 KB of tables + 24 KB of epilogue staging + barriers
+    // (224 KB of the 227 KB an sm_100 CTA can own).  SWIZZLE_128B needs the stage bases 1024 B aligned.
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_base = smem;                                                  // kAStages x 32 KB
     uint8_t* b_base = smem + kAStages * kAStageBytes;                        // kBStages x 64 KB
@@ -229,7 +249,8 @@ pw_mma_kernel(const MmaArgs a) {
     // (scale, shift) of its 32 channels, double-buffered; per epilogue warp a copy of the tile's bias
     float2* s_ab = reinterpret_cast<float2*>(b_base + kBStages * kBStageBytes);   // [kProdWarps][2][32]
     float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 64);    // [kEpiWarps][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kEpiWarps * kMaxTileN);
+    float* s_stage = s_bias + kEpiWarps * kMaxTileN;                     // [kStgBufs][16][128], 1024 B aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kStgBufs * kStgFloats);
     uint64_t* full_bar = bars;                       // [kAStages]  8 transform warps + the TMA thread (+tx bytes)
     uint64_t* empty_bar = full_bar + kAStages;       // [kAStages]  one tcgen05.commit
     uint64_t* tfull_bar = empty_bar + kAStages;      // [2]
@@ -454,6 +475,9 @@ pw_mma_kernel(const MmaArgs a) {
         const int q = warp;                 // TMEM lane quarter of this warp
         const size_t Ls = (size_t)a.L;
         const int nchunks = a.tile_n / kEpiChunk;
+        // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
+        constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
+        int stg_i = 0;
         uint32_t ti = 0;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
@@ -475,7 +499,7 @@ pw_mma_kernel(const MmaArgs a) {
             if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
             float st_s = 0.f, st_q = 0.f;
-            if (MODE != 0) {               // pull this tile's residual / gate rows into L2 while the main loop runs
+            if (MODE == 1 || MODE == 2) {  // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
                 if (lq < a.L) {
                     const float* e0 = ep - lane;               // position lq of row 0
@@ -540,15 +564,54 @@ pw_mma_kernel(const MmaArgs a) {
                     }
                 }
             };
-            issue_ex(EA, 0);
-            mbar_wait(&tfull_bar[acc], aphase);
-            tc_fence_after();
+            if constexpr (kBulk) {
+                // Staged exit: a chunk's [16 channels][128 positions] goes to a shared-memory tile (lane =
+                // position: conflict-free rows) and leaves as ONE TMA tensor store (or fp32 reduce-add, for the
+                // in-place skip connection).  Nothing waits on global memory; the tensor map clips ragged
+                // position tiles and padded channels.  One 128-thread barrier per chunk; thread 0 issues.
+                mbar_wait(&tfull_bar[acc], aphase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < nchunks; c += 2) {
-                issue_ex(EB, c + 1);
-                do_chunk(EA, c);
-                issue_ex(EA, c + 2);
-                do_chunk(EB, c + 1);
+                for (int c = 0; c < nchunks; ++c) {
+                    if (ncols - c * kEpiChunk <= 0) break;         // padded output channels: nothing to store
+                    tmem_ld16(t_acc + (uint32_t)(c * kEpiChunk), R);
+                    float* const buf = s_stage + stg_i * kStgFloats;
+                    stg_i = stg_i == kStgBufs - 1 ? 0 : stg_i + 1;
+                    const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiChunk);
+                    float* const bp = buf + q * 32 + lane;
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j4 = 0; j4 < kEpiChunk / 4; ++j4) {
+                        const float4 bv = b4[j4];
+                        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j4 * 4 + u;
+                            const float o = __uint_as_float(R[j]) + bb[u];
+                            bp[j * 128] = o;
+                            if (STATS) { if (valid) { st_s += o; st_q = fmaf(o, o, st_q); } }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    // before anyone refills the NEXT buffer, the store that read it two chunks ago must be done
+                    if (tid == 0) bulk_wait_read<kStgBufs - 2>();
+                    epi_bar_sync();
+                    if (tid == 0) {
+                        tma_reduce_add_3d(&ymap, buf, tc.l0, tc.n0 + c * kEpiChunk, tc.sample);
+                        bulk_commit();
+                    }
+                }
+            } else {
+                issue_ex(EA, 0);
+                mbar_wait(&tfull_bar[acc], aphase);
+                tc_fence_after();
+    #pragma unroll 1
+                for (int c = 0; c < nchunks; c += 2) {
+                    issue_ex(EB, c + 1);
+                    do_chunk(EA, c);
+                    issue_ex(EA, c + 2);
+                    do_chunk(EB, c + 1);
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
@@ -563,6 +626,7 @@ pw_mma_kernel(const MmaArgs a) {
         }
     }
 
+    if (tid == 0) bulk_wait_all();              // staged output tiles have left shared memory and are written
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
@@ -599,9 +663,42 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
 
 constexpr size_t kMmaSmemBytes = (size_t)kAStages * kAStageBytes + (size_t)kBStages * kBStageBytes +
                                  kProdWarps * 64 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
+                                 (size_t)kStgBufs * kStgFloats * sizeof(float) +
                                  (2 * kAStages + 4 + 2) * sizeof(uint64_t);
 static_assert(kEpiChunk == 16, "tmem_ld16 is hard-wired in the epilogue");
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
+
+// Tensor map of the fp32 output [samples][M][L] with a [1][16][128] box (the epilogue's staging tile).
+// cuTensorMapEncodeTiled is a pure host-side encoder; it is fetched through the runtime so that the library
+// carries no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+static int make_output_map(CUtensorMap* tm, float* y, int samples, int M, int L, bool needed) {
+    memset(tm, 0, sizeof(*tm));
+    if (!needed) return SDR_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return SDR_ERR_CUDA;
+    const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)M, (cuuint64_t)samples};
+    const cuuint64_t strides[2] = {(cuuint64_t)L * 4, (cuuint64_t)L * M * 4};        // bytes, dims 1..2
+    const cuuint32_t box[3] = {(cuuint32_t)kTileM, (cuuint32_t)kEpiChunk, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SDR_OK : SDR_ERR_UNSUPPORTED;
+}
 
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
                          const float* residual, const float* gate, int gate_channels,
@@ -629,13 +726,17 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
     const int grid = (int)(tiles < sms ? tiles : sms);
     const bool act = nin.prelu != nullptr;
-    const int mode = epilogue == 1 ? 2 : (residual ? 1 : 0);
+    // in-place skip connection (every U-ConvBlock's res_conv): the residual add happens in L2 (bulk reduce-add)
+    const bool inplace = SDR_MMA_BULK && residual == y && (reinterpret_cast<uintptr_t>(y) % 16) == 0;
+    const int mode = epilogue == 1 ? 2 : (residual ? (inplace ? 3 : 1) : 0);
     const bool stats = stats_out != nullptr;
+    CUtensorMap ymap;
+    if (int rc = make_output_map(&ymap, y, samples, M, L, mode == 3)) return rc;
 #define SDR_MMA_CASE(A, MD, ST)                                                                                   \
     if (act == A && mode == MD && stats == ST) {                                                                  \
         if (cudaFuncSetAttribute(pw_mma_kernel<false, A, MD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                  (int)kMmaSmemBytes) != cudaSuccess) return SDR_ERR_CUDA;                         \
-        pw_mma_kernel<false, A, MD, ST><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);                             \
+        pw_mma_kernel<false, A, MD, ST><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a, ymap);                             \
         return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;                                         \
     }
     SDR_MMA_CASE(false, 0, false) SDR_MMA_CASE(false, 0, true)
@@ -644,6 +745,8 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     SDR_MMA_CASE(true, 1, false)  SDR_MMA_CASE(true, 1, true)
     SDR_MMA_CASE(false, 2, false) SDR_MMA_CASE(false, 2, true)
     SDR_MMA_CASE(true, 2, false)  SDR_MMA_CASE(true, 2, true)
+    SDR_MMA_CASE(false, 3, false) SDR_MMA_CASE(false, 3, true)
+    SDR_MMA_CASE(true, 3, false)  SDR_MMA_CASE(true, 3, true)
 #undef SDR_MMA_CASE
     return SDR_ERR_UNSUPPORTED;
 }
@@ -685,14 +788,16 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
     const int grid = (int)(tiles < sms ? tiles : sms);
+    CUtensorMap ymap;
+    if (int rc = make_output_map(&ymap, enc, B, N, L, false)) return rc;
     if (stats) {
         if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
             return SDR_ERR_CUDA;
-        pw_mma_kernel<true, false, 0, true><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+        pw_mma_kernel<true, false, 0, true><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a, ymap);
     } else {
         if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
             return SDR_ERR_CUDA;
-        pw_mma_kernel<true, false, 0, false><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a);
+        pw_mma_kernel<true, false, 0, false><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a, ymap);
     }
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }

@@ -156,7 +156,7 @@ def test_pointwise(samples, M, K, L, mode):
         nin = norm_in()
         fx = x
     want = torch.einsum("mk,skl->sml", W.double(), fx.double()) + bias.double().view(1, -1, 1)
-    if mode == "res":
+    if mode in ("res", "res_out"):
         want = want + residual.double()
         res_ptr = p(y)
     else:
@@ -296,6 +296,9 @@ def test_mixture_consistency(kind):
     (3, 42, 1024, 200, "plain"),          # decoder GEMM: 42 rows zero-padded to one 128-wide tile
     (2, 300, 128, 332, "res"),            # 300 rows -> padded to 384 = 3 tiles of 128, last one partial
     (2, 160, 64, 64, "plain_stats"),      # padded to 256: one 256-wide tile with 96 padding columns
+    (2, 256, 512, 640, "res_out"),        # skip connection written out of place (register epilogue)
+    (2, 300, 128, 332, "res_out"),
+    (3, 256, 256, 36, "res"),             # L < 128 and not a multiple of 32: clipped bulk rows
 ])
 def test_pointwise_tensor_core(samples, M, K, L, mode):
     """tcgen05 path (bf16x3 split, fp32 accumulate) against an fp64 reference."""
@@ -319,11 +322,12 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
     if mode == "norm":
         nin = norm_in(stats_in, gamma, beta, None, K * L)
         fx = ref_norm(x.double(), gamma.double(), beta.double())
-    elif mode == "res":
+    elif mode in ("res", "res_out"):
         nin = norm_in(stats_in, gamma, beta, slope, K * L)
         fx = ref_norm(x.double(), gamma.double(), beta.double(), slope.double())
         residual = torch.randn(samples, M, L, generator=g).to(DEV)
-        y = residual.clone()
+        if mode == "res":
+            y = residual.clone()              # in place: y is its own residual (L2 reduce-add exit)
     elif mode == "mask":
         nin = norm_in(None, None, None, slope, 1.0)
         fx = O.prelu1(x.double(), slope.double())
@@ -334,13 +338,13 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
         nin = norm_in()
         fx = x.double()
     want = torch.einsum("mk,skl->sml", W.double(), fx) + bias.double().view(1, -1, 1)
-    if mode == "res":
+    if mode in ("res", "res_out"):
         want = want + residual.double()
     if mode == "mask":
         idx = torch.arange(M, device=DEV) % gate_ch
         want = torch.relu(want) * gate.double()[:, idx, :]
     want_stats = mode == "plain_stats"
-    N.check(lib.sdr_pointwise_mma(p(x), C.byref(nin), p(wpk), p(bias), p(y) if mode == "res" else p(None),
+    N.check(lib.sdr_pointwise_mma(p(x), C.byref(nin), p(wpk), p(bias), p(y) if mode == "res" else (p(residual) if mode == "res_out" else p(None)),
                                   p(gate), gate_ch, p(y), p(st) if want_stats else p(None),
                                   samples, M, K, L, epi, stream()))
     torch.cuda.synchronize()
