@@ -113,6 +113,11 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, const v
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// global -> shared tensor (TMA) load of one [16 channels][128 positions] box; out-of-range elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -239,7 +244,7 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
 //   STATS:  accumulate (sum, sumsq) of the output
 template <bool WINDOW, bool ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(kMmaThreads, 1)
-pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
+pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // tmap: MODE 3 output, MODE 2 gate
     // 2 x 32 KB A stages + 2 x 64 KB B stages + 8 KB of tables + 24 KB of epilogue staging + barriers
     // (224 KB of the 227 KB an sm_100 CTA can own).  SWIZZLE_128B needs the stage bases 1024 B aligned.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -255,7 +260,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
     uint64_t* empty_bar = full_bar + kAStages;       // [kAStages]  one tcgen05.commit
     uint64_t* tfull_bar = empty_bar + kAStages;      // [2]
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* gfull_bar = tempty_bar + 2;            // [kStgBufs]  gate tile landed (TMA tx bytes)
+    uint64_t* gempty_bar = gfull_bar + kStgBufs;     // [kStgBufs]  all 128 epilogue threads have read it
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gempty_bar + kStgBufs);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
     const int tid = threadIdx.x;
@@ -266,6 +273,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
     if (warp == kTmaWarp && lane == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&full_bar[s], kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
+        for (int s = 0; s < kStgBufs; ++s) { mbar_init(&gfull_bar[s], 1); mbar_init(&gempty_bar[s], kEpiWarps * 32); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
@@ -477,7 +485,33 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
         const int nchunks = a.tile_n / kEpiChunk;
         // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
         constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
+        constexpr bool kGateTma = SDR_MMA_BULK && MODE == 2;    // gate tiles arrive through TMA loads into the staging ring
         int stg_i = 0;
+        uint32_t stg_k = 0;                  // how often the ring wrapped (mbarrier phase of the gate tiles)
+        // MODE 2: thread 0 runs a cursor over this CTA's (tile, chunk) sequence two chunks ahead of the consumers
+        struct GateCur { int tile, c, nch, b; uint32_t k; TileCoord tc; } gcur{};
+        auto gate_nch = [&](const TileCoord& t) { return min(nchunks, (min(a.tile_n, a.M - t.n0) + kEpiChunk - 1) / kEpiChunk); };
+        auto gate_issue = [&]() {
+            if (gcur.tile >= a.num_tiles) return;
+            if (gcur.k > 0) mbar_wait(&gempty_bar[gcur.b], (gcur.k - 1) & 1);    // its previous content has been read
+            mbar_arrive_expect_tx(&gfull_bar[gcur.b], kStgFloats * sizeof(float));
+            tma_load_3d(s_stage + gcur.b * kStgFloats, &tmap, &gfull_bar[gcur.b], gcur.tc.l0,
+                        (gcur.tc.n0 % a.gate_channels) + gcur.c * kEpiChunk, gcur.tc.sample);
+            if (++gcur.b == kStgBufs) { gcur.b = 0; ++gcur.k; }
+            if (++gcur.c == gcur.nch) {
+                gcur.c = 0;
+                gcur.tile += gridDim.x;
+                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile); gcur.nch = gate_nch(gcur.tc); }
+            }
+        };
+        if constexpr (kGateTma) {
+            if (tid == 0) {
+                gcur.tile = blockIdx.x;
+                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile); gcur.nch = gate_nch(gcur.tc); }
+                gate_issue();
+                gate_issue();
+            }
+        }
         uint32_t ti = 0;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
@@ -499,7 +533,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
             if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
             float st_s = 0.f, st_q = 0.f;
-            if (MODE == 1 || MODE == 2) {  // pull this tile's residual / gate rows into L2 while the main loop runs
+            if (MODE == 1 || (MODE == 2 && !kGateTma)) {  // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
                 if (lq < a.L) {
                     const float* e0 = ep - lane;               // position lq of row 0
@@ -597,8 +631,56 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap ymap) {
                     if (tid == 0) bulk_wait_read<kStgBufs - 2>();
                     epi_bar_sync();
                     if (tid == 0) {
-                        tma_reduce_add_3d(&ymap, buf, tc.l0, tc.n0 + c * kEpiChunk, tc.sample);
+                        tma_reduce_add_3d(&tmap, buf, tc.l0, tc.n0 + c * kEpiChunk, tc.sample);
                         bulk_commit();
+                    }
+                }
+            } else if constexpr (kGateTma) {
+                // ReLU * gate: the gate rows of a chunk were fetched by TMA into the staging ring (two chunks
+                // ahead, across tile boundaries), so no global load sits on the accumulator's way out.
+                const int nch = min(nchunks, (ncols + kEpiChunk - 1) / kEpiChunk);
+                float* yo = a.y + out_row0;
+                mbar_wait(&tfull_bar[acc], aphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c) {
+                    if (tid == 0) gate_issue();                    // chunk (this + 2)
+                    tmem_ld16(t_acc + (uint32_t)(c * kEpiChunk), R);
+                    const float* gp = s_stage + stg_i * kStgFloats + q * 32 + lane;
+                    mbar_wait(&gfull_bar[stg_i], stg_k & 1);
+                    float E[kEpiChunk];
+#pragma unroll
+                    for (int j = 0; j < kEpiChunk; ++j) E[j] = gp[j * 128];
+                    mbar_arrive(&gempty_bar[stg_i]);
+                    if (++stg_i == kStgBufs) { stg_i = 0; ++stg_k; }
+                    const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiChunk);
+                    const int jmax = ncols - c * kEpiChunk;
+                    tmem_ld_wait();
+                    if (valid) {
+                        if (jmax >= kEpiChunk) {
+#pragma unroll
+                            for (int j4 = 0; j4 < kEpiChunk / 4; ++j4) {
+                                const float4 bv = b4[j4];
+                                const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int j = j4 * 4 + u;
+                                    const float o = fmaxf(__uint_as_float(R[j]) + bb[u], 0.f) * E[j];
+                                    *yo = o;
+                                    yo += Ls;
+                                    if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < kEpiChunk; ++j) {
+                                if (j < jmax) {
+                                    const float o = fmaxf(__uint_as_float(R[j]) + sb[c * kEpiChunk + j], 0.f) * E[j];
+                                    yo[(size_t)j * Ls] = o;
+                                    if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
+                                }
+                            }
+                        }
                     }
                 }
             } else {
@@ -664,7 +746,7 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
 constexpr size_t kMmaSmemBytes = (size_t)kAStages * kAStageBytes + (size_t)kBStages * kBStageBytes +
                                  kProdWarps * 64 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
                                  (size_t)kStgBufs * kStgFloats * sizeof(float) +
-                                 (2 * kAStages + 4 + 2) * sizeof(uint64_t);
+                                 (2 * kAStages + 4 + 2 * kStgBufs + 2) * sizeof(uint64_t);
 static_assert(kEpiChunk == 16, "tmem_ld16 is hard-wired in the epilogue");
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
@@ -685,7 +767,7 @@ static EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
-static int make_output_map(CUtensorMap* tm, float* y, int samples, int M, int L, bool needed) {
+static int make_tile_map(CUtensorMap* tm, const float* y, int samples, int M, int L, bool needed) {
     memset(tm, 0, sizeof(*tm));
     if (!needed) return SDR_OK;
     EncodeTiledFn enc = encode_tiled_fn();
@@ -694,7 +776,7 @@ static int make_output_map(CUtensorMap* tm, float* y, int samples, int M, int L,
     const cuuint64_t strides[2] = {(cuuint64_t)L * 4, (cuuint64_t)L * M * 4};        // bytes, dims 1..2
     const cuuint32_t box[3] = {(cuuint32_t)kTileM, (cuuint32_t)kEpiChunk, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, dims, strides, box, estr,
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(y), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SDR_OK : SDR_ERR_UNSUPPORTED;
@@ -730,8 +812,10 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     const bool inplace = SDR_MMA_BULK && residual == y && (reinterpret_cast<uintptr_t>(y) % 16) == 0;
     const int mode = epilogue == 1 ? 2 : (residual ? (inplace ? 3 : 1) : 0);
     const bool stats = stats_out != nullptr;
-    CUtensorMap ymap;
-    if (int rc = make_output_map(&ymap, y, samples, M, L, mode == 3)) return rc;
+    if (SDR_MMA_BULK && mode == 2 && (reinterpret_cast<uintptr_t>(gate) % 16) != 0) return SDR_ERR_UNSUPPORTED;   // TMA address
+    CUtensorMap ymap;      // MODE 3: the in-place output; MODE 2: the gate tensor [samples][gate_channels][L]
+    if (int rc = mode == 2 ? make_tile_map(&ymap, gate, samples, gate_channels, L, SDR_MMA_BULK)
+                           : make_tile_map(&ymap, y, samples, M, L, mode == 3)) return rc;
 #define SDR_MMA_CASE(A, MD, ST)                                                                                   \
     if (act == A && mode == MD && stats == ST) {                                                                  \
         if (cudaFuncSetAttribute(pw_mma_kernel<false, A, MD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
@@ -789,7 +873,7 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
     const int grid = (int)(tiles < sms ? tiles : sms);
     CUtensorMap ymap;
-    if (int rc = make_output_map(&ymap, enc, B, N, L, false)) return rc;
+    if (int rc = make_tile_map(&ymap, enc, B, N, L, false)) return rc;
     if (stats) {
         if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
             return SDR_ERR_CUDA;

@@ -299,6 +299,8 @@ def test_mixture_consistency(kind):
     (2, 256, 512, 640, "res_out"),        # skip connection written out of place (register epilogue)
     (2, 300, 128, 332, "res_out"),
     (3, 256, 256, 36, "res"),             # L < 128 and not a multiple of 32: clipped bulk rows
+    (3, 512, 128, 200, "mask"),           # ragged last position tile: zero-filled gate boxes
+    (20, 512, 64, 1280, "mask"),          # many tiles per CTA: the gate ring wraps across tile boundaries
 ])
 def test_pointwise_tensor_core(samples, M, K, L, mode):
     """tcgen05 path (bf16x3 split, fp32 accumulate) against an fp64 reference."""
