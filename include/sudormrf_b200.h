@@ -187,6 +187,39 @@ int sdr_tac(const float* x, const float* const* params, float* o, double* stats_
 int sdr_overlap_add(const float* frames, const float* mix_or_null, float* out,
                     int B, int SA, int K, int L, int64_t T, sdr_stream stream);
 
+/* ---- the steps either side of the forward -------- */
+
+/* Per-row (mean, unbiased std) of a waveform batch: wav [rows, T] ->
+ * mean_std [rows][2] fp32 (README.md:101-102: `x.mean(-1)`, `x.std(-1)`).
+ * scratch: rows * 2 doubles of device memory.                                */
+int sdr_utterance_stats(const float* wav, float* mean_std, int rows, int64_t T,
+                        void* scratch, sdr_stream stream);
+
+/* The README inference recipe as ONE call (README.md:100-114):
+ *   m, s = wav.mean(-1), wav.std(-1);  x = (wav - m) / (s + 1e-9)
+ *   est  = model(x.unsqueeze(1)) * s + m
+ *   [est = mixture_consistency.apply(est, x.unsqueeze(1))]      (uniform)
+ * wav [B,1,T] -> out [B,S,T].  Mono models only (in_audio_channels == 1).
+ * Workspace: sdr_separate_workspace_bytes (forward workspace + the
+ * normalised copy of the batch).                                             */
+size_t sdr_separate_workspace_bytes(const sdr_config* cfg, int B, int64_t T);
+int sdr_separate(const sdr_config* cfg, const void* packed, const float* wav, float* out,
+                 int B, int64_t T, int apply_mixture_consistency,
+                 void* workspace, size_t workspace_bytes, sdr_stream stream);
+
+/* Permutation-invariant SI-SDR of a batch (dnn/losses/sisdr.py:66-194,
+ * PermInvariantSISDR.forward with return_individual_results=True,
+ * backward_loss=False): est, target [B,S,T], mixture [B,1,T] (needed only for
+ * improvement != 0) -> best[b] = max over permutations of the source-mean
+ * SI-SNR (minus the batch-mean SI-SNR of the mixture when improvement != 0),
+ * perm_index[b] = index of that permutation in itertools.permutations(range(S))
+ * order.  1 <= S <= 4.  eps as in the reference's forward (default 1e-9).     */
+size_t sdr_pit_sisdr_scratch_bytes(int B, int S);
+int sdr_pit_sisdr(const float* est, const float* target, const float* mixture_or_null,
+                  float* best, int32_t* perm_index, int B, int S, int64_t T,
+                  int zero_mean, int improvement, double eps,
+                  void* scratch, sdr_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,8 @@ reference tree (``/root/reference``):
   improved_sudormrf.py   = sudo_rm_rf/dnn/models/improved_sudormrf.py
   groupcomm_sudormrf_v2.py = sudo_rm_rf/dnn/models/groupcomm_sudormrf_v2.py
   mixture_consistency.py = sudo_rm_rf/dnn/experiments/utils/mixture_consistency.py
+  README.md              = the reference's README (inference recipe, lines 100-114)
+  sisdr.py               = sudo_rm_rf/dnn/losses/sisdr.py (validation metric)
 
 Parity pinning: the reference ships NO golden vectors for this path,
 so the oracle is pinned against outputs of the reference itself, generated in
@@ -344,6 +346,60 @@ def mixture_consistency(est: Tensor, mix: Tensor,
         raise ValueError(
             "Invalid mixture consistency weight type: {}".format(mix_weights_type))
     return est + w * resid
+
+
+# --------------------------------------------------------------------------
+# the steps either side of the forward
+# --------------------------------------------------------------------------
+def separate(cfg: Config, sd: Dict[str, Tensor], wav: Tensor,
+             apply_mixture_consistency: bool = False, dtype=torch.float32) -> Tensor:
+    """The README inference recipe, README.md:100-114.  wav [B, T] -> [B, S, T]."""
+    wav = wav.to(dtype)
+    std = wav.std(-1, keepdim=True)                      # README.md:101 (unbiased)
+    mean = wav.mean(-1, keepdim=True)                    # README.md:102
+    x = (wav - mean) / (std + 1e-9)                      # README.md:103
+    rec = forward(cfg, sd, x.unsqueeze(1), dtype=dtype)  # README.md:106
+    rec = (rec * std.unsqueeze(1)) + mean.unsqueeze(1)   # README.md:109
+    if apply_mixture_consistency:                        # README.md:113-114
+        rec = mixture_consistency(rec, x.unsqueeze(1))
+    return rec
+
+
+def pit_sisdr(pr: Tensor, tgt: Tensor, mix: Optional[Tensor] = None, zero_mean: bool = False,
+              improvement: bool = False, eps: float = 1e-9):
+    """PermInvariantSISDR.forward with backward_loss=False, return_individual_results=True
+    (sisdr.py:95-194).  Returns (best [B], index of the best permutation [B]) with the
+    permutations in itertools.permutations(range(S)) order (sisdr.py:87-89)."""
+    import itertools
+    n = min(pr.shape[-1], tgt.shape[-1])                                  # sisdr.py:96-102
+    if mix is not None:
+        n = min(n, mix.shape[-1])
+        mix = mix[:, :, :n]
+    pr, tgt = pr[:, :, :n], tgt[:, :, :n]
+    if zero_mean:                                                         # sisdr.py:104-111
+        pr = pr - pr.mean(-1, keepdim=True)
+        tgt = tgt - tgt.mean(-1, keepdim=True)
+        if mix is not None:
+            mix = mix - mix.mean(-1, keepdim=True)
+
+    def dot(a, b):                                                        # sisdr.py:114-116
+        return torch.sum(a * b, dim=-1, keepdim=True)
+
+    def permuted(p, t, tt):                                               # sisdr.py:118-126
+        s_t = dot(p, t) / (tt + eps) * t
+        e_t = p - s_t
+        return 10 * torch.log10(dot(s_t, s_t) / (dot(e_t, e_t) + eps))
+
+    S = pr.shape[1]
+    tt = dot(tgt, tgt)                                                    # sisdr.py:134
+    cols = [permuted(pr[:, list(perm), :], tgt, tt)                       # sisdr.py:136-142
+            for perm in itertools.permutations(range(S))]
+    allp = torch.cat(cols, -1)
+    best, idx = torch.max(allp.mean(-2), -1)                              # sisdr.py:143
+    if improvement:                                                       # sisdr.py:145-150
+        base = permuted(mix.repeat(1, S, 1), tgt, tt)
+        best = best - base.mean()
+    return best, idx
 
 
 # --------------------------------------------------------------------------

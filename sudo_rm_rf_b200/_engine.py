@@ -191,6 +191,40 @@ def forward(model, wav: torch.Tensor, mixture_consistency: bool = False) -> torc
     return out
 
 
+def separate(model, wav: torch.Tensor, mixture_consistency: bool = False) -> torch.Tensor:
+    """The README inference recipe (reference README.md:100-114) as one native call:
+    per-utterance normalisation, forward, rescale with the mixture's std / mean and, optionally, the
+    uniform mixture-consistency projection against the normalised mixture (as the README applies it to
+    the GroupComm checkpoints).  ``wav`` is ``[B, T]`` (as in the README) or ``[B, 1, T]``; returns
+    ``[B, S, T]`` fp32 on the same device."""
+    lib = N.lib()
+    cfg = make_config(model)
+    if wav.dim() == 2:
+        wav = wav.unsqueeze(1)
+    x = _check_input(model, cfg, wav)
+    if cfg.in_audio_channels != 1:
+        raise RuntimeError("separate() follows the README recipe, which is written for mono mixtures")
+    device = x.device
+    B, _, T = x.shape
+    with torch.cuda.device(device):
+        packed = packed_weights(model, cfg, device)
+        st = _state(model, device)
+        ws_bytes = lib.sdr_separate_workspace_bytes(C.byref(cfg), B, T)
+        if ws_bytes == 0:
+            raise N.NativeError("bad model configuration (sdr_separate_workspace_bytes returned 0)")
+        if st.workspace is None or st.workspace.numel() < ws_bytes:
+            st.workspace = None
+            st.graphs.clear()
+            st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        out = torch.empty((B, cfg.num_sources, T), dtype=torch.float32, device=device)
+        N.check(lib.sdr_separate(C.byref(cfg), C.c_void_p(packed.data_ptr()),
+                                 C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                 B, T, 1 if mixture_consistency else 0,
+                                 C.c_void_p(st.workspace.data_ptr()), st.workspace.numel(),
+                                 _stream_ptr(device)), "sdr_separate")
+    return out
+
+
 def forward_host(model, host_wav: torch.Tensor, host_out: torch.Tensor = None,
                  mixture_consistency: bool = False, device=None, use_graph: bool = True) -> torch.Tensor:
     """End-to-end call with HOST buffers: H2D copy, forward, D2H copy, all enqueued on the current

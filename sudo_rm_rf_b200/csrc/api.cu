@@ -16,10 +16,16 @@ int launch_merge(const float* const*, const NormIn*, int, float*, double*, int, 
 int launch_pointwise_ffma(const float*, const NormIn&, const float*, const float*, const float*, const float*, int,
                           float*, double*, int, int, int, int, int, cudaStream_t);
 int launch_encoder(const float*, const float*, float*, double*, int, int, long long, int, int, int, cudaStream_t);
-int launch_overlap_add(const float*, const float*, float*, int, int, int, int, long long, cudaStream_t);
+int launch_overlap_add(const float*, const float*, const float2*, float*, int, int, int, int, long long, cudaStream_t);
 int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
+// pre/post steps (prepost.cu)
+int launch_utterance_stats(const float*, double*, float2*, int, long long, cudaStream_t);
+int launch_normalize_rows(const float*, const float2*, float*, int, long long, cudaStream_t);
+size_t pit_sisdr_scratch_bytes(int B, int S);
+int launch_pit_sisdr(const float*, const float*, const float*, float*, int*, int, int, long long, int, int, double,
+                     void*, cudaStream_t);
 // tensor-core path (pointwise_mma.cu)
 bool pointwise_mma_eligible(int M, int K);
 size_t pointwise_mma_packed_bytes(int M, int K);
@@ -188,7 +194,8 @@ static Plan make_plan(const Layout& l, int B, long long T) {
 
 
 static int forward_impl(const Layout& l, const float* pk, const float* mixture, float* out,
-                        int B, long long T, int apply_mc, char* ws, cudaStream_t st) {
+                        int B, long long T, int apply_mc, char* ws, cudaStream_t st,
+                        const float2* rescale = nullptr) {
     const Plan p = make_plan(l, B, T);
     const int L = p.L, D = l.D;
     double* stats = reinterpret_cast<double*>(ws + p.o_stats);
@@ -270,7 +277,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     SDR_TRY(pointwise(masked, none, pk + l.dec_wt, l.dec_pk ? pk + l.dec_pk : nullptr, nullptr, nullptr, nullptr, 0,
                       frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
     const float* mix = (apply_mc && l.A == 1) ? mixture : nullptr;
-    SDR_TRY(launch_overlap_add(frames, mix, out, B, l.S * l.A, l.K, L, T, st));
+    SDR_TRY(launch_overlap_add(frames, mix, rescale, out, B, l.S * l.A, l.K, L, T, st));
     return SDR_OK;
 }
 
@@ -492,7 +499,64 @@ int sdr_overlap_add(const float* frames, const float* mix_or_null, float* out, i
                     int L, int64_t T, sdr_stream stream) {
     if (!frames || !out) return SDR_ERR_BAD_ARGUMENT;
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
-    return launch_overlap_add(frames, mix_or_null, out, B, SA, K, L, T, static_cast<cudaStream_t>(stream));
+    return launch_overlap_add(frames, mix_or_null, nullptr, out, B, SA, K, L, T, static_cast<cudaStream_t>(stream));
+}
+
+// ---- steps either side of the forward ----
+
+// layout of the extra region appended to the forward workspace by sdr_separate
+static size_t separate_extra_bytes(const Layout& l, int B, long long T) {
+    const size_t wav = ((size_t)B * l.A * T * sizeof(float) + 255) & ~(size_t)255;
+    const size_t sums = ((size_t)B * 2 * sizeof(double) + 255) & ~(size_t)255;
+    const size_t ms = ((size_t)B * sizeof(float2) + 255) & ~(size_t)255;
+    return wav + sums + ms;
+}
+
+int sdr_utterance_stats(const float* wav, float* mean_std, int rows, int64_t T, void* scratch, sdr_stream stream) {
+    if (!scratch || reinterpret_cast<uintptr_t>(scratch) % 8 || reinterpret_cast<uintptr_t>(mean_std) % 8)
+        return SDR_ERR_BAD_ARGUMENT;
+    return launch_utterance_stats(wav, static_cast<double*>(scratch), reinterpret_cast<float2*>(mean_std), rows, T,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+size_t sdr_separate_workspace_bytes(const sdr_config* cfg, int B, int64_t T) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok || B <= 0 || T <= 0) return 0;
+    return make_plan(l, B, T).total + separate_extra_bytes(l, B, T);
+}
+
+int sdr_separate(const sdr_config* cfg, const void* packed, const float* wav, float* out,
+                 int B, int64_t T, int apply_mixture_consistency,
+                 void* workspace, size_t workspace_bytes, sdr_stream stream) {
+    const Layout l = make_layout(cfg);
+    SDR_TRY(check_forward_args(l, B, T));
+    if (l.A != 1) return SDR_ERR_UNSUPPORTED;            // the README recipe is written for mono mixtures
+    if (!packed || !wav || !out || !workspace) return SDR_ERR_BAD_ARGUMENT;
+    const size_t fwd = make_plan(l, B, T).total;
+    if (workspace_bytes < fwd + separate_extra_bytes(l, B, T)) return SDR_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 || reinterpret_cast<uintptr_t>(packed) % 16)
+        return SDR_ERR_BAD_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    float* norm = reinterpret_cast<float*>(ws + fwd);
+    char* cur = ws + fwd + (((size_t)B * T * sizeof(float) + 255) & ~(size_t)255);
+    double* sums = reinterpret_cast<double*>(cur);
+    cur += ((size_t)B * 2 * sizeof(double) + 255) & ~(size_t)255;
+    float2* ms = reinterpret_cast<float2*>(cur);
+    SDR_TRY(launch_utterance_stats(wav, sums, ms, B, T, st));                    // README.md:101-102
+    SDR_TRY(launch_normalize_rows(wav, ms, norm, B, T, st));                     // README.md:103
+    return forward_impl(l, static_cast<const float*>(packed), norm, out, B, T,   // README.md:106,109,113-114
+                        apply_mixture_consistency, ws, st, ms);
+}
+
+size_t sdr_pit_sisdr_scratch_bytes(int B, int S) { return pit_sisdr_scratch_bytes(B, S); }
+
+int sdr_pit_sisdr(const float* est, const float* target, const float* mixture_or_null, float* best, int32_t* perm_index,
+                  int B, int S, int64_t T, int zero_mean, int improvement, double eps,
+                  void* scratch, sdr_stream stream) {
+    if (scratch && reinterpret_cast<uintptr_t>(scratch) % 8) return SDR_ERR_BAD_ARGUMENT;
+    return launch_pit_sisdr(est, target, mixture_or_null, best, perm_index, B, S, T, zero_mean, improvement, eps,
+                            scratch, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

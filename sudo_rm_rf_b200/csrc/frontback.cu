@@ -109,7 +109,7 @@ constexpr int kMaxSrc = 16;
 
 __global__ void __launch_bounds__(256)
 overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ mix,
-                   float* __restrict__ out, int SA, int K, int L, long long T) {
+                   const float2* __restrict__ rescale, float* __restrict__ out, int SA, int K, int L, long long T) {
     const int hop = K / 2;
     const long long tau = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -120,12 +120,16 @@ overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ m
     tlo = tlo <= 0 ? 0 : (tlo + hop - 1) / hop;
     float est[kMaxSrc];
     float sum = 0.f;
+    // separate(): undo the per-utterance input normalisation, est * std + mean (README.md:109), before the
+    // mixture-consistency projection, which the README applies to the rescaled estimates (README.md:113-114)
+    const float2 rs = rescale ? rescale[b] : make_float2(0.f, 1.f);
     for (int s = 0; s < SA; ++s) {
         float acc = 0.f;
         for (long long t = tlo; t <= thi && t < L; ++t) {
             const int j = (int)(tau + hop - hop * t);
             acc += __ldg(frames + ((size_t)b * SA * K + (size_t)s * K + j) * L + t);
         }
+        if (rescale) acc = __fadd_rn(__fmul_rn(acc, rs.y), rs.x);
         est[s] = acc;
         sum += acc;
     }
@@ -134,12 +138,12 @@ overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ m
     for (int s = 0; s < SA; ++s) out[((size_t)b * SA + s) * T + tau] = est[s] + corr;
 }
 
-int launch_overlap_add(const float* frames, const float* mix, float* out, int B, int SA, int K,
-                       int L, long long T, cudaStream_t st) {
+int launch_overlap_add(const float* frames, const float* mix, const float2* rescale, float* out, int B, int SA,
+                       int K, int L, long long T, cudaStream_t st) {
     if (B <= 0 || SA <= 0 || K < 3 || L <= 0 || T <= 0) return SDR_ERR_BAD_ARGUMENT;
     if (SA > kMaxSrc || B > 65535) return SDR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)((T + 255) / 256), (unsigned)B);
-    overlap_add_kernel<<<grid, 256, 0, st>>>(frames, mix, out, SA, K, L, T);
+    overlap_add_kernel<<<grid, 256, 0, st>>>(frames, mix, rescale, out, SA, K, L, T);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

@@ -86,9 +86,15 @@ class GroupCommSudoRmRf(nn.Module):
         """[B, in_audio_channels, T] -> [B, num_sources*in_audio_channels, T]."""
         return _engine.forward(self, input_wav, mixture_consistency=False)
 
-    def separate(self, input_wav, mixture_consistency=True):
+    def separate(self, input_wav, mixture_consistency=True, normalize=False):
         """forward() followed by the uniform mixture consistency the reference applies
-        to this model family (README.md:113-114), fused into the decoder epilogue."""
+        to this model family (README.md:113-114), fused into the decoder epilogue.
+
+        ``normalize=True``: the whole README recipe on the device (README.md:100-114): raw
+        mixture ``[B, T]`` / ``[B, 1, T]`` -> per-utterance normalisation -> model -> rescale
+        with the mixture's std and mean -> mixture consistency against the normalised mixture."""
+        if normalize:
+            return _engine.separate(self, input_wav, mixture_consistency=mixture_consistency)
         return _engine.forward(self, input_wav, mixture_consistency=mixture_consistency)
 
     def forward_host(self, host_wav, host_out=None, mixture_consistency=False):

@@ -142,9 +142,16 @@ class SuDORMRF(nn.Module):
         """[B, 1, T] mixture -> [B, num_sources, T] estimates (fp32, same device)."""
         return _engine.forward(self, input_wav, mixture_consistency=False)
 
-    def separate(self, input_wav, mixture_consistency=False):
+    def separate(self, input_wav, mixture_consistency=False, normalize=False):
         """forward() with the uniform mixture-consistency projection
-        (mixture_consistency.py:14-36) fused into the decoder epilogue."""
+        (mixture_consistency.py:14-36) fused into the decoder epilogue.
+
+        ``normalize=True`` runs the whole README recipe (reference README.md:100-114) on the
+        device: ``input_wav`` is the raw mixture ``[B, T]`` or ``[B, 1, T]``; it is normalised per
+        utterance (mean, unbiased std), separated, and the estimates are rescaled with the
+        mixture's std and mean (then, optionally, projected onto the normalised mixture)."""
+        if normalize:
+            return _engine.separate(self, input_wav, mixture_consistency=mixture_consistency)
         return _engine.forward(self, input_wav, mixture_consistency=mixture_consistency)
 
     def forward_host(self, host_wav, host_out=None, mixture_consistency=False):

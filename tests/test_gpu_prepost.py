@@ -1,0 +1,166 @@
+"""GPU parity of the steps either side of the forward, through the public
+API (which calls the C-ABI): per-utterance statistics, `separate(..., normalize=True)` = the README
+recipe, and the PIT SI-SDR metric.  Checked against the reference's golden vectors, the CPU oracle,
+and size-independent properties at the benchmark shape."""
+import ctypes as C
+import itertools
+
+import pytest
+import torch
+
+import sudo_rm_rf_b200 as P
+from sudo_rm_rf_b200 import _native as N
+from sudo_rm_rf_b200 import sisdr as S
+from oracle import sudormrf_oracle as O
+from test_prepost_oracle import SEPARATE, load_separate, load_sisdr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-3
+
+
+def build(variant, kw, sd):
+    cls = P.SuDORMRF if variant == "improved" else P.GroupCommSudoRmRf
+    m = cls(**kw)
+    m.load_state_dict(sd)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("rows,T", [(1, 1000), (5, 517), (32, 32000), (3, 7), (2, 100003)])
+def test_utterance_stats(rows, T):
+    g = torch.Generator().manual_seed(rows * 1000 + T)
+    wav = (torch.randn(rows, T, generator=g) * torch.logspace(-2, 1, rows).view(rows, 1)
+           + torch.linspace(-3, 50, rows).view(rows, 1)).to(DEV)          # DC up to 50x the AC level
+    ms = torch.full((rows, 2), float("nan"), device=DEV)
+    scratch = torch.empty(rows * 2, dtype=torch.float64, device=DEV)
+    N.check(N.lib().sdr_utterance_stats(C.c_void_p(wav.data_ptr()), C.c_void_p(ms.data_ptr()), rows, T,
+                                        C.c_void_p(scratch.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    want_mean = wav.double().mean(-1)
+    want_std = wav.double().std(-1)
+    assert torch.allclose(ms[:, 0].double(), want_mean, rtol=2e-7, atol=0)
+    assert torch.allclose(ms[:, 1].double(), want_std, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("path", SEPARATE, ids=lambda p: p.split("prepost_separate_")[1][:-4])
+def test_separate_golden(path):
+    """README.md:100-114 end to end against the reference's own outputs."""
+    meta, sd, wav, plain, with_mc = load_separate(path)
+    m = build(meta["variant"], meta["kwargs"], sd)
+    with torch.no_grad():
+        got = m.separate(wav.to(DEV), mixture_consistency=False, normalize=True)
+        assert got.shape == plain.shape and got.dtype == torch.float32 and got.is_cuda
+        e = O.parity_errors(got, plain)
+        print("separate golden", meta["name"], "rel_max %.2e rel_l2 %.2e" % e)
+        assert max(e) < TOL, e
+        got = m.separate(wav.to(DEV).unsqueeze(1), mixture_consistency=True, normalize=True)   # [B,1,T] also accepted
+        e = O.parity_errors(got, with_mc)
+        assert max(e) < TOL, e
+        # and it really is the composition of the public pieces
+        x = wav.to(DEV)
+        xn = (x - x.mean(-1, keepdim=True)) / (x.std(-1, keepdim=True) + 1e-9)
+        ref = m(xn.unsqueeze(1)) * x.std(-1, keepdim=True).unsqueeze(1) + x.mean(-1, keepdim=True).unsqueeze(1)
+        assert max(O.parity_errors(m.separate(x, normalize=True, mixture_consistency=False), ref)) < TOL
+
+
+def test_separate_vs_oracle_mid_size():
+    kw = dict(out_channels=128, in_channels=256, num_blocks=2, upsampling_depth=4,
+              enc_kernel_size=21, enc_num_basis=256, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    sd = O.make_state_dict(cfg, seed=3, perturbed=True)
+    g = torch.Generator().manual_seed(9)
+    scale = torch.tensor([0.01, 1.0, 30.0]).view(3, 1)
+    wav = torch.randn(3, 8013, generator=g) * scale + 0.2 * scale
+    want = O.separate(cfg, sd, wav, apply_mixture_consistency=True)
+    m = build("improved", kw, sd)
+    with torch.no_grad():
+        got = m.separate(wav.to(DEV), mixture_consistency=True, normalize=True)
+    e = O.parity_errors(got, want)
+    assert max(e) < TOL, e
+
+
+def test_separate_gain_and_offset_equivariance_full_size():
+    """separate(a * wav + c) == a * separate(wav) + c for a > 0 (benchmark shape: 32 x 4 s)."""
+    kw = dict(out_channels=256, in_channels=512, num_blocks=16, upsampling_depth=5,
+              enc_kernel_size=21, enc_num_basis=512, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    m = build("improved", kw, O.make_state_dict(cfg, seed=1, perturbed=True))
+    g = torch.Generator().manual_seed(2)
+    wav = torch.randn(32, 32000, generator=g).to(DEV)
+    a = torch.logspace(-1, 1, 32, device=DEV).view(32, 1)
+    c = torch.linspace(-0.2, 0.2, 32, device=DEV).view(32, 1)
+    with torch.no_grad():
+        y0 = m.separate(wav, normalize=True)
+        y1 = m.separate(a * wav + c, normalize=True)
+    want = a.unsqueeze(1) * y0 + c.unsqueeze(1)
+    e = O.parity_errors(y1, want)
+    print("separate equivariance rel_max %.2e rel_l2 %.2e" % e)
+    assert max(e) < TOL, e
+    assert torch.isfinite(y1).all()
+
+
+def test_separate_refuses_multichannel():
+    kw = dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=3, enc_kernel_size=11,
+              enc_num_basis=16, num_sources=2, group_size=8, in_audio_channels=2)
+    m = P.GroupCommSudoRmRf(**kw).to(DEV).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m.separate(torch.randn(2, 2, 333, device=DEV), normalize=True)
+
+
+@pytest.mark.parametrize("ci", range(6))
+def test_pit_sisdr_golden(ci):
+    c, t = load_sisdr()[ci]
+    fn = S.PermInvariantSISDR(batch_size=c["B"], zero_mean=c["zero_mean"], n_sources=c["S"],
+                              backward_loss=False, improvement=c["improvement"],
+                              return_individual_results=True)
+    with torch.no_grad():
+        best, perms = fn(t["est"].to(DEV), t["tgt"].to(DEV), initial_mixtures=t["mix"].to(DEV),
+                         return_best_permutation=True)
+    assert best.shape == t["best"].shape and best.is_cuda
+    assert torch.allclose(best.cpu(), t["best"], atol=1e-3, rtol=0), (best.cpu() - t["best"]).abs().max()
+    assert torch.equal(perms.cpu(), t["perms"])
+    loss = S.PermInvariantSISDR(batch_size=c["B"], zero_mean=c["zero_mean"], n_sources=c["S"],
+                                backward_loss=True, improvement=c["improvement"],
+                                return_individual_results=False)
+    with torch.no_grad():
+        scalar = loss(t["est"].to(DEV), t["tgt"].to(DEV), initial_mixtures=t["mix"].to(DEV))
+    assert abs(float(scalar) - float(t["loss"][0])) < 1e-3
+
+
+def test_pit_sisdr_full_size_vs_oracle_and_permutation_property():
+    """Validation-loop shape (32 x 2 x 4 s): against the CPU oracle, and permuting the estimates'
+    source order must permute the reported assignment and leave the score unchanged."""
+    g = torch.Generator().manual_seed(11)
+    B, Sn, T = 32, 2, 32000
+    tgt = torch.randn(B, Sn, T, generator=g)
+    est = tgt + torch.randn(B, Sn, T, generator=g) * torch.logspace(-2, 0.5, B).view(B, 1, 1)
+    swap = torch.rand(B, generator=g) < 0.5
+    est[swap] = est[swap][:, [1, 0]]
+    mix = tgt.sum(1, keepdim=True)
+    want, widx = O.pit_sisdr(est, tgt, mix, zero_mean=True, improvement=True)
+    fn = S.PermInvariantSISDR(batch_size=B, zero_mean=True, n_sources=Sn, backward_loss=False,
+                              improvement=True, return_individual_results=True)
+    with torch.no_grad():
+        best, perms = fn(est.to(DEV), tgt.to(DEV), initial_mixtures=mix.to(DEV), return_best_permutation=True)
+        best2, perms2 = fn(est[:, [1, 0]].to(DEV), tgt.to(DEV), initial_mixtures=mix.to(DEV),
+                           return_best_permutation=True)
+    assert torch.allclose(best.cpu(), want, atol=1e-3, rtol=0), (best.cpu() - want).abs().max()
+    allp = list(itertools.permutations(range(Sn)))
+    assert [tuple(int(v) for v in r) for r in perms.cpu()] == [allp[int(i)] for i in widx]
+    assert torch.allclose(best, best2, atol=1e-5, rtol=0)
+    assert torch.equal(perms2.cpu(), 1 - perms.cpu())
+    assert torch.equal(perms.cpu()[:, 0] == 1, swap)
+
+
+def test_pit_sisdr_argument_errors():
+    fn = S.PermInvariantSISDR(n_sources=2, improvement=True)
+    with pytest.raises(RuntimeError):
+        fn(torch.zeros(2, 2, 100), torch.zeros(2, 2, 100))                       # CPU tensors: no CPU path
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        fn(torch.zeros(2, 2, 100, device=DEV), torch.zeros(2, 2, 100, device=DEV))   # SI-SDRi without the mixture
+    with pytest.raises(RuntimeError):
+        fn(torch.zeros(2, 2, 100, device=DEV, requires_grad=True), torch.zeros(2, 2, 100, device=DEV),
+           initial_mixtures=torch.zeros(2, 1, 100, device=DEV))                  # metric only: no autograd
+    five = S.PermInvariantSISDR(n_sources=5)
+    with torch.no_grad(), pytest.raises(N.NativeError):
+        five(torch.zeros(1, 5, 50, device=DEV), torch.zeros(1, 5, 50, device=DEV))
