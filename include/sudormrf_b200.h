@@ -207,6 +207,19 @@ int sdr_separate(const sdr_config* cfg, const void* packed, const float* wav, fl
                  int B, int64_t T, int apply_mixture_consistency,
                  void* workspace, size_t workspace_bytes, sdr_stream stream);
 
+/* The same recipe for a RAGGED batch: B utterances of different lengths that
+ * share one padded length T (a multiple of hop * 2^depth, sdr_padded_length),
+ * stored zero-padded as wav [B,1,T]; lengths[b] (device, int64) = true length.
+ * Statistics use the first lengths[b] samples only, the padding stays zero,
+ * i.e. every row is computed exactly as the reference computes that utterance
+ * alone (improved_sudormrf.py:303-318 pads it to the same T).  rescale = 0
+ * skips `est * std + mean` (utils/simple_whamr_evaluation.py:141-148 evaluates
+ * the normalised estimates).  out [B,S,T]: row b is valid up to lengths[b].   */
+int sdr_separate_ragged(const sdr_config* cfg, const void* packed, const float* wav,
+                        const int64_t* lengths, float* out, int B, int64_t T,
+                        int apply_mixture_consistency, int rescale,
+                        void* workspace, size_t workspace_bytes, sdr_stream stream);
+
 /* Permutation-invariant SI-SDR of a batch (dnn/losses/sisdr.py:66-194,
  * PermInvariantSISDR.forward with return_individual_results=True,
  * backward_loss=False): est, target [B,S,T], mixture [B,1,T] (needed only for

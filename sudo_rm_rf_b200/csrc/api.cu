@@ -21,8 +21,8 @@ int launch_mixture_consistency(const float*, const float*, float*, int, int, lon
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
 // pre/post steps (prepost.cu)
-int launch_utterance_stats(const float*, double*, float2*, int, long long, cudaStream_t);
-int launch_normalize_rows(const float*, const float2*, float*, int, long long, cudaStream_t);
+int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
+int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
 size_t pit_sisdr_scratch_bytes(int B, int S);
 int launch_pit_sisdr(const float*, const float*, const float*, float*, int*, int, int, long long, int, int, double,
                      void*, cudaStream_t);
@@ -516,7 +516,7 @@ int sdr_utterance_stats(const float* wav, float* mean_std, int rows, int64_t T, 
     if (!scratch || reinterpret_cast<uintptr_t>(scratch) % 8 || reinterpret_cast<uintptr_t>(mean_std) % 8)
         return SDR_ERR_BAD_ARGUMENT;
     return launch_utterance_stats(wav, static_cast<double*>(scratch), reinterpret_cast<float2*>(mean_std), rows, T,
-                                  static_cast<cudaStream_t>(stream));
+                                  nullptr, static_cast<cudaStream_t>(stream));
 }
 
 size_t sdr_separate_workspace_bytes(const sdr_config* cfg, int B, int64_t T) {
@@ -525,9 +525,9 @@ size_t sdr_separate_workspace_bytes(const sdr_config* cfg, int B, int64_t T) {
     return make_plan(l, B, T).total + separate_extra_bytes(l, B, T);
 }
 
-int sdr_separate(const sdr_config* cfg, const void* packed, const float* wav, float* out,
-                 int B, int64_t T, int apply_mixture_consistency,
-                 void* workspace, size_t workspace_bytes, sdr_stream stream) {
+static int separate_impl(const sdr_config* cfg, const void* packed, const float* wav, const int64_t* lengths,
+                         float* out, int B, int64_t T, int apply_mixture_consistency, int rescale,
+                         void* workspace, size_t workspace_bytes, sdr_stream stream) {
     const Layout l = make_layout(cfg);
     SDR_TRY(check_forward_args(l, B, T));
     if (l.A != 1) return SDR_ERR_UNSUPPORTED;            // the README recipe is written for mono mixtures
@@ -543,10 +543,29 @@ int sdr_separate(const sdr_config* cfg, const void* packed, const float* wav, fl
     double* sums = reinterpret_cast<double*>(cur);
     cur += ((size_t)B * 2 * sizeof(double) + 255) & ~(size_t)255;
     float2* ms = reinterpret_cast<float2*>(cur);
-    SDR_TRY(launch_utterance_stats(wav, sums, ms, B, T, st));                    // README.md:101-102
-    SDR_TRY(launch_normalize_rows(wav, ms, norm, B, T, st));                     // README.md:103
+    const long long* len = reinterpret_cast<const long long*>(lengths);
+    SDR_TRY(launch_utterance_stats(wav, sums, ms, B, T, len, st));               // README.md:101-102
+    SDR_TRY(launch_normalize_rows(wav, ms, norm, B, T, len, st));                // README.md:103
     return forward_impl(l, static_cast<const float*>(packed), norm, out, B, T,   // README.md:106,109,113-114
-                        apply_mixture_consistency, ws, st, ms);
+                        apply_mixture_consistency, ws, st, rescale ? ms : nullptr);
+}
+
+int sdr_separate(const sdr_config* cfg, const void* packed, const float* wav, float* out,
+                 int B, int64_t T, int apply_mixture_consistency,
+                 void* workspace, size_t workspace_bytes, sdr_stream stream) {
+    return separate_impl(cfg, packed, wav, nullptr, out, B, T, apply_mixture_consistency, 1,
+                         workspace, workspace_bytes, stream);
+}
+
+int sdr_separate_ragged(const sdr_config* cfg, const void* packed, const float* wav, const int64_t* lengths,
+                        float* out, int B, int64_t T, int apply_mixture_consistency, int rescale,
+                        void* workspace, size_t workspace_bytes, sdr_stream stream) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok) return SDR_ERR_BAD_CONFIG;
+    if (!lengths) return SDR_ERR_BAD_ARGUMENT;
+    if (T <= 0 || padded_len(l, T) != T) return SDR_ERR_BAD_ARGUMENT;   // the bucket width is a padded length
+    return separate_impl(cfg, packed, wav, lengths, out, B, T, apply_mixture_consistency, rescale,
+                         workspace, workspace_bytes, stream);
 }
 
 size_t sdr_pit_sisdr_scratch_bytes(int B, int S) { return pit_sisdr_scratch_bytes(B, S); }

@@ -19,14 +19,24 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 // ---------------------------------------------------------------------------
 // utterance moments: sums[row] = (sum_t x, sum_t x^2), fp64
 // grid = rows * chunks, 256 threads; the caller zeroes `sums`.
+// Rows are T apart; with `lengths` (ragged batch, zero-padded to T) only the first
+// lengths[row] samples of a row are the utterance.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ long long row_length(const long long* lengths, int row, long long T) {
+    if (!lengths) return T;
+    const long long n = lengths[row];
+    return n < 0 ? 0 : (n > T ? T : n);
+}
+
 __global__ void __launch_bounds__(256)
-row_moments_kernel(const float* __restrict__ x, double* __restrict__ sums, long long T, int chunks) {
+row_moments_kernel(const float* __restrict__ x, double* __restrict__ sums, long long T, int chunks,
+                   const long long* __restrict__ lengths) {
     __shared__ double red[2][8];
     const int row = blockIdx.x / chunks, chunk = blockIdx.x - row * chunks;
-    const long long per = (T + chunks - 1) / chunks;
+    const long long Tr = row_length(lengths, row, T);
+    const long long per = (Tr + chunks - 1) / chunks;
     const long long t0 = (long long)chunk * per;
-    const long long t1 = t0 + per < T ? t0 + per : T;
+    const long long t1 = t0 + per < Tr ? t0 + per : Tr;
     const float* xr = x + (size_t)row * T;
     double s = 0.0, q = 0.0;
     for (long long t = t0 + threadIdx.x; t < t1; t += 256) {
@@ -48,10 +58,11 @@ row_moments_kernel(const float* __restrict__ x, double* __restrict__ sums, long 
 }
 
 // (mean, unbiased std) per row as fp32, the precision the reference carries them in
-__global__ void row_mean_std_kernel(const double* __restrict__ sums, float2* __restrict__ ms, int rows, long long T) {
+__global__ void row_mean_std_kernel(const double* __restrict__ sums, float2* __restrict__ ms, int rows, long long T,
+                                    const long long* __restrict__ lengths) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    const double n = (double)T;
+    const double n = (double)row_length(lengths, r, T);
     const double s = sums[2 * (size_t)r], q = sums[2 * (size_t)r + 1];
     const double mean = s / n;
     double var = (q - s * mean) / (n - 1.0);          // torch.std default: Bessel's correction (T == 1 -> NaN, as torch)
@@ -61,16 +72,19 @@ __global__ void row_mean_std_kernel(const double* __restrict__ sums, float2* __r
 
 // y = (x - mean) / (std + 1e-9)      (README.md:103)
 __global__ void __launch_bounds__(256)
-normalize_rows_kernel(const float* __restrict__ x, const float2* __restrict__ ms, float* __restrict__ y, long long T) {
+normalize_rows_kernel(const float* __restrict__ x, const float2* __restrict__ ms, float* __restrict__ y, long long T,
+                      const long long* __restrict__ lengths) {
     const int row = blockIdx.y;
     const float2 m = ms[row];
     const float den = m.y + 1e-9f;
     const size_t base = (size_t)row * T;
+    const long long Tr = row_length(lengths, row, T);      // beyond the utterance: the zero padding stays zero
     for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < T; t += (long long)gridDim.x * 256)
-        y[base + t] = (__ldg(x + base + t) - m.x) / den;
+        y[base + t] = t < Tr ? (__ldg(x + base + t) - m.x) / den : 0.f;
 }
 
-int launch_utterance_stats(const float* wav, double* sums, float2* mean_std, int rows, long long T, cudaStream_t st) {
+int launch_utterance_stats(const float* wav, double* sums, float2* mean_std, int rows, long long T,
+                           const long long* lengths, cudaStream_t st) {
     if (!wav || !sums || !mean_std || rows <= 0 || T <= 0) return SDR_ERR_BAD_ARGUMENT;
     if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * rows, st) != cudaSuccess) return SDR_ERR_CUDA;
     int chunks = (int)((T + 8191) / 8192);
@@ -78,18 +92,19 @@ int launch_utterance_stats(const float* wav, double* sums, float2* mean_std, int
     if (chunks > 64) chunks = 64;
     const long long grid = (long long)rows * chunks;
     if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
-    row_moments_kernel<<<(unsigned)grid, 256, 0, st>>>(wav, sums, T, chunks);
-    row_mean_std_kernel<<<(rows + 127) / 128, 128, 0, st>>>(sums, mean_std, rows, T);
+    row_moments_kernel<<<(unsigned)grid, 256, 0, st>>>(wav, sums, T, chunks, lengths);
+    row_mean_std_kernel<<<(rows + 127) / 128, 128, 0, st>>>(sums, mean_std, rows, T, lengths);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
-int launch_normalize_rows(const float* wav, const float2* mean_std, float* out, int rows, long long T, cudaStream_t st) {
+int launch_normalize_rows(const float* wav, const float2* mean_std, float* out, int rows, long long T,
+                          const long long* lengths, cudaStream_t st) {
     if (!wav || !mean_std || !out || rows <= 0 || T <= 0) return SDR_ERR_BAD_ARGUMENT;
     if (rows > 65535) return SDR_ERR_UNSUPPORTED;
     long long gx = (T + 256 * 4 - 1) / (256 * 4);
     if (gx < 1) gx = 1;
     if (gx > 4096) gx = 4096;
-    normalize_rows_kernel<<<dim3((unsigned)gx, (unsigned)rows), 256, 0, st>>>(wav, mean_std, out, T);
+    normalize_rows_kernel<<<dim3((unsigned)gx, (unsigned)rows), 256, 0, st>>>(wav, mean_std, out, T, lengths);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

@@ -1,0 +1,44 @@
+"""Host logic of the bucketed corpus inference (sudo_rm_rf_b200/corpus.py): CPU only."""
+import random
+
+import pytest
+
+from oracle import sudormrf_oracle as O
+from sudo_rm_rf_b200.corpus import padded_length, plan_buckets
+
+
+def test_padded_length_is_the_reference_rule():
+    for depth in (1, 3, 5, 6):
+        for k in (11, 21, 41):
+            cfg = O.Config(enc_kernel_size=k, upsampling_depth=depth)
+            q = (k // 2) * 2 ** depth
+            for T in (1, 7, q - 1, q, q + 1, 3 * q, 3 * q + 5, 32000, 32079):
+                assert padded_length(T, q) == O.padded_length(cfg, T)
+    with pytest.raises(ValueError):
+        padded_length(0, 320)
+
+
+def test_plan_covers_every_utterance_once_and_buckets_share_a_padded_length():
+    rnd = random.Random(3)
+    lengths = [rnd.randint(1, 40000) for _ in range(500)] + [320, 640, 640, 319, 321]
+    plan = plan_buckets(lengths, 320, 32)
+    seen = []
+    last_tp = 0
+    for tp, idx in plan:
+        assert 1 <= len(idx) <= 32
+        assert tp % 320 == 0 and tp >= last_tp
+        last_tp = tp
+        assert all(padded_length(lengths[i], 320) == tp for i in idx)
+        assert idx == sorted(idx)                      # corpus order inside a batch
+        seen += idx
+    assert sorted(seen) == list(range(len(lengths)))
+
+
+def test_plan_splits_large_buckets_and_is_deterministic():
+    lengths = [1000] * 70 + [5] * 3
+    plan = plan_buckets(lengths, 320, 32)
+    assert [(tp, len(idx)) for tp, idx in plan] == [(320, 3), (1280, 32), (1280, 32), (1280, 6)]
+    assert plan == plan_buckets(lengths, 320, 32)
+    assert plan_buckets([], 320, 8) == []
+    with pytest.raises(ValueError):
+        plan_buckets([10], 320, 0)

@@ -164,3 +164,46 @@ def test_pit_sisdr_argument_errors():
     five = S.PermInvariantSISDR(n_sources=5)
     with torch.no_grad(), pytest.raises(N.NativeError):
         five(torch.zeros(1, 5, 50, device=DEV), torch.zeros(1, 5, 50, device=DEV))
+
+
+CORPUS_MODELS = [
+    ("improved", dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=3,
+                      enc_kernel_size=21, enc_num_basis=64, num_sources=2)),
+    ("groupcomm", dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+                       enc_kernel_size=21, enc_num_basis=48, num_sources=3, group_size=4)),
+]
+
+
+@pytest.mark.parametrize("variant,kw", CORPUS_MODELS, ids=[c[0] for c in CORPUS_MODELS])
+@pytest.mark.parametrize("mc", [False, True])
+def test_separate_corpus_equals_one_at_a_time(variant, kw, mc):
+    """Bucketed ragged batches reproduce the reference's one-utterance-at-a-time loop
+    (simple_whamr_evaluation.py:138-148 / README.md:100-114)."""
+    from sudo_rm_rf_b200.corpus import separate_corpus
+    cfg = O.Config(variant=variant, **kw)
+    sd = O.make_state_dict(cfg, seed=5, perturbed=True)
+    m = build(variant, kw, sd)
+    q = cfg.n_least_samples_req
+    g = torch.Generator().manual_seed(17)
+    lengths = [q, q - 1, 1500, 1501, 1502, 37, 2 * q, 2 * q + 1, 5000, 4999, 1499, q + 3, 4990]
+    wavs = [torch.randn(T, generator=g) * (0.1 + 3 * torch.rand(1, generator=g)) + 0.1 * torch.randn(1, generator=g)
+            for T in lengths]
+    with torch.no_grad():
+        got = separate_corpus(m, wavs, max_batch=3, mixture_consistency=mc)
+        assert len(got) == len(wavs)
+        for w, y in zip(wavs, got):
+            assert y.shape == (cfg.num_sources, w.shape[0]) and y.is_cuda
+            alone = m.separate(w.to(DEV)[None], mixture_consistency=mc, normalize=True)[0]
+            e = O.parity_errors(y[None], alone[None])
+            assert max(e) < 1e-5, (w.shape[0], e)
+        # against the CPU oracle for a few of them
+        for i in (0, 3, 5, 8):
+            want = O.separate(cfg, sd, wavs[i][None], apply_mixture_consistency=mc)[0]
+            assert max(O.parity_errors(got[i][None], want[None])) < TOL
+        # rescale=False: estimates of the normalised mixture (what the evaluation script scores)
+        raw = separate_corpus(m, wavs[:5], max_batch=4, mixture_consistency=mc, rescale=False)
+        for w, y in zip(wavs[:5], raw):
+            x = w.to(DEV)
+            xn = ((x - x.mean()) / (x.std() + 1e-9))[None, None]
+            want = m.separate(xn, mixture_consistency=mc)[0]
+            assert max(O.parity_errors(y[None], want[None])) < 1e-4
