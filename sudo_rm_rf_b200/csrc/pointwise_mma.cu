@@ -37,8 +37,21 @@ constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
 constexpr int kBHalfMax = kMaxTileN * 128;
 constexpr int kAStageBytes = 2 * kAHalf;                     // 32 KB: hi + lo
 constexpr int kBStageBytes = 2 * kBHalfMax;                  // 64 KB: hi + lo
+#ifndef SDR_MMA_EPI_WARPS
+#define SDR_MMA_EPI_WARPS 4             // epilogue warps of the plain-store exit (MODE 0).  8 = two per TMEM lane quarter, each
+#endif                                  // owning half of the tile's columns: a round-2 experiment, compiled but NOT measured yet
+#if SDR_MMA_EPI_WARPS == 4
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
+#define SDR_MMA_THREADS(MODE) kMmaThreads
+#else
+static_assert(SDR_MMA_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
+constexpr int kEpiWarps = 4, kProdWarps = 8;                  // kEpiWarps: the staged exits and the shared-memory carve-up
+// warp roles: [0, EW) epilogue, EW MMA issuer, EW + 1 weight TMA, [EW + 2, EW + 10) operand transform
+constexpr int mma_epi_warps(int mode) { return mode == 0 ? SDR_MMA_EPI_WARPS : kEpiWarps; }
+constexpr int mma_threads(int mode) { return 32 * (mma_epi_warps(mode) + 2 + kProdWarps); }   // 448 or 576
+#define SDR_MMA_THREADS(MODE) mma_threads(MODE)
+#endif
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
 #ifndef SDR_MMA_BULK
 #define SDR_MMA_BULK 1                  // 1: the in-place skip connection (mode 3) leaves through staging tiles + TMA reduce-add
@@ -243,7 +256,7 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
 //           3 = in-place skip connection (y == residual): y += acc + bias as a bulk reduce-add in L2
 //   STATS:  accumulate (sum, sumsq) of the output
 template <bool WINDOW, bool ACT, int MODE, bool STATS>
-__global__ void __launch_bounds__(kMmaThreads, 1)
+__global__ void __launch_bounds__(SDR_MMA_THREADS(MODE), 1)
 pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // tmap: MODE 3 output, MODE 2 gate
     // 2 x 32 KB A stages + 2 x 64 KB B stages + 8 KB of tables + 24 KB of epilogue staging + barriers
     // (224 KB of the 227 KB an sm_100 CTA can own).  SWIZZLE_128B needs the stage bases 1024 B aligned.
@@ -265,6 +278,10 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gempty_bar + kStgBufs);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
+#if SDR_MMA_EPI_WARPS != 4
+    constexpr int EW = mma_epi_warps(MODE), EG = EW / 4;
+    constexpr int kMmaWarp = EW, kTmaWarp = EW + 1, kProdWarp0 = EW + 2;
+#endif
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int KB = a.K / kBlockK;
@@ -272,7 +289,11 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
 
     if (warp == kTmaWarp && lane == 0) {
         for (int s = 0; s < kAStages; ++s) { mbar_init(&full_bar[s], kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
+#if SDR_MMA_EPI_WARPS == 4
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
+#else
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW * 32); }
+#endif
         for (int s = 0; s < kStgBufs; ++s) { mbar_init(&gfull_bar[s], 1); mbar_init(&gempty_bar[s], kEpiWarps * 32); }
         fence_barrier_init();
     }
@@ -480,9 +501,17 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
+#if SDR_MMA_EPI_WARPS == 4
         const int q = warp;                 // TMEM lane quarter of this warp
         const size_t Ls = (size_t)a.L;
         const int nchunks = a.tile_n / kEpiChunk;
+#else
+        const int q = warp & 3;             // TMEM lane quarter of this warp
+        // with two warps per quarter (EG == 2) warp w owns the columns [col0, col0 + tile_n / 2) of the tile
+        const int col0 = (warp >> 2) * (a.tile_n / EG);
+        const size_t Ls = (size_t)a.L;
+        const int nchunks = a.tile_n / kEpiChunk / EG;
+#endif
         // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
         constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
         constexpr bool kGateTma = SDR_MMA_BULK && MODE == 2;    // gate tiles arrive through TMA loads into the staging ring
@@ -518,6 +547,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
             const TileCoord tc = decode_tile(a, tile);
+#if SDR_MMA_EPI_WARPS == 4
             float* const sb = s_bias + q * kMaxTileN;          // this warp's private copy of the tile's bias
             const int ncols = min(a.tile_n, a.M - tc.n0);      // real output channels in this tile (< tile_n: padding)
             __syncwarp();                                      // the warp is done with the previous tile's bias
@@ -527,11 +557,26 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
             const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0) * Ls + l;       // (m = n0, l)
+#else
+            float* const sb = s_bias + warp * (kMaxTileN / EG);    // this warp's private copy of its columns' bias
+            const int ncols = min(a.tile_n, a.M - tc.n0) - col0;   // real output channels among this warp's columns
+            __syncwarp();                                      // the warp is done with the previous tile's bias
+            for (int j = lane; j < a.tile_n / EG; j += 32)
+                sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + col0 + j) : 0.f;
+            __syncwarp();
+            const int l = tc.l0 + q * 32 + lane;
+            const bool valid = l < a.L;
+            const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0 + col0) * Ls + l;   // (m = n0 + col0, l)
+#endif
             // MODE 1: residual (may alias y: in-place skip connection); MODE 2: gate operand of this tile
             const float* ep = nullptr;
             if (MODE == 1) ep = a.residual + out_row0;
             if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
+#if SDR_MMA_EPI_WARPS == 4
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
+#else
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN + col0);
+#endif
             float st_s = 0.f, st_q = 0.f;
             if (MODE == 1 || (MODE == 2 && !kGateTma)) {  // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
@@ -820,7 +865,7 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     if (act == A && mode == MD && stats == ST) {                                                                  \
         if (cudaFuncSetAttribute(pw_mma_kernel<false, A, MD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                  (int)kMmaSmemBytes) != cudaSuccess) return SDR_ERR_CUDA;                         \
-        pw_mma_kernel<false, A, MD, ST><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a, ymap);                             \
+        pw_mma_kernel<false, A, MD, ST><<<grid, SDR_MMA_THREADS(MD), kMmaSmemBytes, st>>>(a, ymap);                             \
         return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;                                         \
     }
     SDR_MMA_CASE(false, 0, false) SDR_MMA_CASE(false, 0, true)
@@ -877,11 +922,11 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     if (stats) {
         if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
             return SDR_ERR_CUDA;
-        pw_mma_kernel<true, false, 0, true><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a, ymap);
+        pw_mma_kernel<true, false, 0, true><<<grid, SDR_MMA_THREADS(0), kMmaSmemBytes, st>>>(a, ymap);
     } else {
         if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
             return SDR_ERR_CUDA;
-        pw_mma_kernel<true, false, 0, false><<<grid, kMmaThreads, kMmaSmemBytes, st>>>(a, ymap);
+        pw_mma_kernel<true, false, 0, false><<<grid, SDR_MMA_THREADS(0), kMmaSmemBytes, st>>>(a, ymap);
     }
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
