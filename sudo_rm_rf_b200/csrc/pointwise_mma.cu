@@ -37,6 +37,9 @@ constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
 constexpr int kBHalfMax = kMaxTileN * 128;
 constexpr int kAStageBytes = 2 * kAHalf;                     // 32 KB: hi + lo
 constexpr int kBStageBytes = 2 * kBHalfMax;                  // 64 KB: hi + lo
+#ifndef SDR_MMA_LEAN_PRODUCER
+#define SDR_MMA_LEAN_PRODUCER 0         // 1: transform loop with pointer-bumped cursors and the (scale, shift) table read before
+#endif                                  // the stage wait (round-2 experiment from the ncu source view; compiled, NOT measured yet)
 #ifndef SDR_MMA_EPI_WARPS
 #define SDR_MMA_EPI_WARPS 4             // epilogue warps of the plain-store exit (MODE 0).  8 = two per TMEM lane quarter, each
 #endif                                  // owning half of the tile's columns: a round-2 experiment, compiled but NOT measured yet
@@ -373,6 +376,122 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             }
         };
 
+#if SDR_MMA_LEAN_PRODUCER
+        // The ncu source view of the loop below (profiles/r01d_tma_epilogue.md): 400 instructions per k-block and warp, of
+        // which only ~200 are the transform; the rest re-derives three (tile, k-block) cursors, 64-bit row addresses and
+        // bounds tests per row, and a quarter of the stall samples sit on the table LDS feeding each channel's first FFMA.
+        // Here: one pointer per cursor (bumped by 64 channel rows inside a tile, recomputed at a tile change), one
+        // predicate per step, and the table read before the stage wait.  Same data, same barrier protocol.
+        if constexpr (!WINDOW) {
+            const size_t kstep = (size_t)kBlockK * Ls;                       // floats between consecutive k-blocks of a row
+            // row 0 (channel pw*8 of k-block kb) at this lane's 4 positions; null: outside the sample (zero operand)
+            auto row0 = [&](const TileCoord& t, int kb) -> const float* {
+                const int l = t.l0 + p4;
+                return l < a.L ? a.x + (((size_t)t.sample * a.K + (size_t)kb * kBlockK + pw * 8) * Ls + l) : nullptr;
+            };
+            // L2 prefetch address of a step: lane -> (channel row lane & 7, 32-position segment lane >> 3)
+            auto pf0 = [&](const TileCoord& t, int kb) -> const float* {
+                const int l = t.l0 + (lane >> 3) * 32;
+                return l < a.L ? a.x + (((size_t)t.sample * a.K + (size_t)kb * kBlockK + pw * 8 + (lane & 7)) * Ls + l) : nullptr;
+            };
+            int tile = blockIdx.x, kb = 0;
+            if (tile < a.num_tiles) {
+                TileCoord tc = decode_tile(a, tile);
+                const float* cp0 = row0(tc, 0);
+                float4 v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = cp0 ? ldg4(cp0 + (size_t)e * Ls) : make_float4(0.f, 0.f, 0.f, 0.f);
+                Cur c0; c0.tile = tile; c0.kb = 0; c0.tc = tc;
+                Aux aux = load_aux(c0);
+                // prefetch cursor: two steps ahead of the step being transformed
+                int ptile = tile, pkb = 0;
+                const float* pp = pf0(tc, 0);
+                auto pf_advance = [&]() {
+                    if (++pkb == KB) {
+                        pkb = 0;
+                        ptile += gridDim.x;
+                        pp = ptile < a.num_tiles ? pf0(decode_tile(a, ptile), 0) : nullptr;
+                    } else if (pp) {
+                        pp += kstep;
+                    }
+                };
+                pf_advance();
+                if (ptile < a.num_tiles && pp) prefetch_l2(pp);
+                uint32_t it = 0;
+                float mean = 0.f, rstd = 1.f;          // of the current tile's sample
+#pragma unroll 1
+                while (tile < a.num_tiles) {
+                    // next step: same tile -> bump, else decode the CTA's next tile
+                    Cur n; n.tile = tile; n.kb = kb + 1; n.tc = tc;
+                    const float* np = cp0 ? cp0 + kstep : nullptr;
+                    if (n.kb == KB) {
+                        n.kb = 0;
+                        n.tile = tile + gridDim.x;
+                        np = nullptr;
+                        if (n.tile < a.num_tiles) { n.tc = decode_tile(a, n.tile); np = row0(n.tc, 0); }
+                    }
+                    pf_advance();
+                    if (ptile < a.num_tiles && pp) prefetch_l2(pp);
+                    const int stage = it % kAStages;
+                    const uint32_t phase = (it / kAStages) & 1;
+                    {                                  // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
+                        float aa = 1.f, bb = 0.f;
+                        if (has_norm) {
+                            if (kb == 0) {
+                                const double mu = aux.s0 * inv_count;
+                                double var = aux.s1 * inv_count - mu * mu;
+                                var = var < 0.0 ? 0.0 : var;
+                                mean = (float)mu;
+                                rstd = rsqrtf((float)var + kGlnEps);
+                            }
+                            aa = aux.g * rstd;
+                            bb = aux.b - mean * aa;
+                        }
+                        if (lane < 8) my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
+                        aux = load_aux(n);
+                    }
+                    __syncwarp();                      // table visible to the warp (reuse is ordered by the next __syncwarp)
+                    const float2* tab = my_tab + (it & 1) * 8;
+                    float2 abv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) abv[e] = tab[e];               // before the stage wait: latency hidden
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
+                    uint8_t* a_lo = a_hi + kAHalf;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 ab = abv[e];
+                        float y[4] = {fmaf(v[e].x, ab.x, ab.y), fmaf(v[e].y, ab.x, ab.y),
+                                      fmaf(v[e].z, ab.x, ab.y), fmaf(v[e].w, ab.x, ab.y)};
+                        v[e] = np ? ldg4(np + (size_t)e * Ls) : make_float4(0.f, 0.f, 0.f, 0.f);   // refill: next step
+                        if (ACT) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float t = y[u] * slope;
+                                y[u] = slope_le1 ? fmaxf(y[u], t) : fminf(y[u], t);
+                            }
+                        }
+                        uint32_t hb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) hb[u] = __float_as_uint(y[u]) & 0xffff0000u;
+                        const uint32_t h01 = __byte_perm(hb[0], hb[1], 0x7632), h23 = __byte_perm(hb[2], hb[3], 0x7632);
+                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[0] - __uint_as_float(hb[0]), y[1] - __uint_as_float(hb[1]));
+                        const __nv_bfloat162 l23 = __floats2bfloat162_rn(y[2] - __uint_as_float(hb[2]), y[3] - __uint_as_float(hb[3]));
+                        const uint32_t off = lane_off + (uint32_t)e * 128 + ((lane_chunk ^ (uint32_t)e) << 4);
+                        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
+                        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
+                                                                            *reinterpret_cast<const uint32_t*>(&l23));
+                    }
+                    fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    ++it;
+                    tile = n.tile; kb = n.kb; tc = n.tc; cp0 = np;
+                }
+            }
+        } else
+#endif
+        {
         Cur c;
         c.tile = blockIdx.x; c.kb = 0;
         if (c.tile < a.num_tiles) {
@@ -445,6 +564,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                 ++it;
                 c = n;
             }
+        }
         }
     } else if (warp == kTmaWarp) {
         // ===================== B-operand (weights) bulk-TMA producer =====================
