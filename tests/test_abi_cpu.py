@@ -105,3 +105,28 @@ def test_state_dict_roundtrip_and_module_prefix():
     m.load_state_dict({k[len("module."):]: v for k, v in dp.items()})
     for k, v in m.state_dict().items():
         assert torch.equal(v, sd[k])
+
+
+def test_prepost_entry_points_have_no_cpu_path():
+    """separate(normalize=True), separate_corpus and the SI-SDR metric raise on CPU tensors / models
+    (no fallback), and reject what the reference's recipe does not cover."""
+    from sudo_rm_rf_b200 import sisdr
+    from sudo_rm_rf_b200.corpus import separate_corpus
+    m = P.SuDORMRF(16, 32, 1, 2, 21, 16, 2).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.separate(torch.zeros(2, 100), normalize=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        separate_corpus(m, [torch.zeros(50), torch.zeros(70)])
+    with pytest.raises(RuntimeError, match="1-D"):
+        separate_corpus(m, [torch.zeros(1, 50)])
+    assert separate_corpus(m, []) == []
+    metric = sisdr.PermInvariantSISDR(n_sources=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        metric(torch.zeros(1, 2, 10), torch.zeros(1, 2, 10))
+    with pytest.raises(RuntimeError, match="n_sources"):
+        metric(torch.zeros(1, 3, 10), torch.zeros(1, 3, 10))
+    assert metric.permutations == [(0, 1), (1, 0)] or [tuple(int(i) for i in p) for p in metric.permutations] == [(0, 1), (1, 0)]
+    lib = _native.lib()
+    assert lib.sdr_pit_sisdr_scratch_bytes(4, 2) > 0 and lib.sdr_pit_sisdr_scratch_bytes(4, 5) == 0
+    cfg = _native.SdrConfig(0, 1, 16, 32, 1, 2, 21, 16, 2, 1)
+    assert lib.sdr_separate_workspace_bytes(C.byref(cfg), 2, 100) > lib.sdr_workspace_bytes(C.byref(cfg), 2, 100)
