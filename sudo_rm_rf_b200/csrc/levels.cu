@@ -269,6 +269,9 @@ __device__ __forceinline__ float norm_act(float x, const FoldedNorm& f, float sl
 #ifndef SDR_STREAM_HINTS
 #define SDR_STREAM_HINTS 0
 #endif
+#ifndef SDR_DW_PIPELINE
+#define SDR_DW_PIPELINE 0               // 1: wide depthwise kernel with the next run's loads ahead of the arithmetic (experiment)
+#endif
 // SDR_DW_CHAIN (common.cuh): 1 = stride-2 levels of a block in one persistent kernel (experiment, see dw5_chain_kernel)
 // streaming accesses: every byte of these kernels is touched once, so (optionally) keep it out of L1
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
@@ -381,6 +384,130 @@ dw5_wide_kernel(const float* __restrict__ x, NormIn nin,
     }
     block_stats_atomic(acc_s, acc_q, stats_out, sample, s_red);
 }
+
+#if SDR_DW_PIPELINE
+// ---------------------------------------------------------------------------
+// EXPERIMENT (round-2 candidate, compiled only with -DSDR_DW_PIPELINE=1, not measured yet): the same kernel with the
+// loads of run i+1 issued before the arithmetic of run i.  The ncu source view of dw5_wide_kernel<2,0> put 62 % of the
+// stall samples on the first FFMA of each run (four serial load -> compute -> store round trips per thread).
+// ---------------------------------------------------------------------------
+template <int STRIDE>
+struct DwRun {
+    float4 m[STRIDE == 1 ? 2 : 4];
+    float2 l;
+    float2 r;                 // stride 1: two right-halo values; stride 2: r.x only
+    int c, q;
+    bool ok, hl, hr;
+};
+
+template <int STRIDE>
+__device__ __forceinline__ DwRun<STRIDE> dw_load_run(const float* __restrict__ xs, int item, int items, int QR, int Lin) {
+    DwRun<STRIDE> d;
+    d.ok = item < items;
+    d.c = 0; d.q = 0; d.hl = false; d.hr = false;
+    d.l = make_float2(0.f, 0.f); d.r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < (STRIDE == 1 ? 2 : 4); ++i) d.m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.ok) {
+        d.c = item / QR;
+        d.q = item - d.c * QR;
+        const float* xr = xs + (size_t)d.c * Lin + (STRIDE == 1 ? 8 : 16) * d.q;
+#pragma unroll
+        for (int i = 0; i < (STRIDE == 1 ? 2 : 4); ++i) d.m[i] = ld_stream4(xr + 4 * i);
+        d.hl = d.q > 0;
+        if (d.hl) d.l = __ldg(reinterpret_cast<const float2*>(xr - 2));
+        if (STRIDE == 1) {
+            d.hr = d.q < QR - 1;
+            if (d.hr) d.r = __ldg(reinterpret_cast<const float2*>(xr + 8));
+        } else {
+            d.hr = 16 * d.q + 16 < Lin;
+            if (d.hr) d.r.x = __ldg(xr + 16);
+        }
+    }
+    return d;
+}
+
+template <int STRIDE, bool ACT>
+__global__ void __launch_bounds__(kDw8Threads)
+dw5_wide_pipe_kernel(const float* __restrict__ x, NormIn nin,
+                     const float* __restrict__ w5, const float* __restrict__ bias,
+                     float* __restrict__ y, double* __restrict__ stats_out,
+                     int C, int Lin, int Lout, int chunks_per_sample) {
+    __shared__ SampleNorm s_norm;
+    __shared__ float s_red[64];
+    const int sample = blockIdx.x / chunks_per_sample;
+    const int chunk = blockIdx.x - sample * chunks_per_sample;
+    const int QR = Lout >> 3;                 // runs per row
+    const int items = C * QR;                 // per sample
+    const float* xs = x + (size_t)sample * C * Lin;
+    float* ys = y + (size_t)sample * C * Lout;
+    // the first run's loads do not depend on the sample statistics: issue them before the barrier
+    DwRun<STRIDE> cur = dw_load_run<STRIDE>(xs, (chunk * kDw8Items + 0) * kDw8Threads + threadIdx.x, items, QR, Lin);
+    if (threadIdx.x == 0) s_norm = sample_norm(nin, sample);
+    const float slope = ACT ? __ldg(nin.prelu) : 1.f;
+    const bool sle1 = slope <= 1.f;
+    __syncthreads();
+    const SampleNorm sn = s_norm;
+    float acc_s = 0.f, acc_q = 0.f;
+#pragma unroll
+    for (int it = 0; it < kDw8Items; ++it) {
+        DwRun<STRIDE> nxt;
+        if (it + 1 < kDw8Items)
+            nxt = dw_load_run<STRIDE>(xs, (chunk * kDw8Items + it + 1) * kDw8Threads + threadIdx.x, items, QR, Lin);
+        if (cur.ok) {
+            const FoldedNorm f = fold_norm(nin, sn, cur.c);
+            float w[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) w[j] = __ldg(w5 + cur.c * 5 + j);
+            const float b = __ldg(bias + cur.c);
+            float o[8];
+            if (STRIDE == 1) {
+                float v[12];
+                v[0] = cur.hl ? norm_act<ACT>(cur.l.x, f, slope, sle1) : 0.f;
+                v[1] = cur.hl ? norm_act<ACT>(cur.l.y, f, slope, sle1) : 0.f;
+                const float mm[8] = {cur.m[0].x, cur.m[0].y, cur.m[0].z, cur.m[0].w, cur.m[1].x, cur.m[1].y, cur.m[1].z, cur.m[1].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[2 + i] = norm_act<ACT>(mm[i], f, slope, sle1);
+                v[10] = cur.hr ? norm_act<ACT>(cur.r.x, f, slope, sle1) : 0.f;
+                v[11] = cur.hr ? norm_act<ACT>(cur.r.y, f, slope, sle1) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = b;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) a = fmaf(w[j], v[i + j], a);
+                    o[i] = a;
+                }
+            } else {
+                float v[19];
+                v[0] = cur.hl ? norm_act<ACT>(cur.l.x, f, slope, sle1) : 0.f;
+                v[1] = cur.hl ? norm_act<ACT>(cur.l.y, f, slope, sle1) : 0.f;
+                const float mm[16] = {cur.m[0].x, cur.m[0].y, cur.m[0].z, cur.m[0].w, cur.m[1].x, cur.m[1].y, cur.m[1].z, cur.m[1].w,
+                                      cur.m[2 % (STRIDE == 1 ? 2 : 4)].x, cur.m[2 % (STRIDE == 1 ? 2 : 4)].y,
+                                      cur.m[2 % (STRIDE == 1 ? 2 : 4)].z, cur.m[2 % (STRIDE == 1 ? 2 : 4)].w,
+                                      cur.m[3 % (STRIDE == 1 ? 2 : 4)].x, cur.m[3 % (STRIDE == 1 ? 2 : 4)].y,
+                                      cur.m[3 % (STRIDE == 1 ? 2 : 4)].z, cur.m[3 % (STRIDE == 1 ? 2 : 4)].w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[2 + i] = norm_act<ACT>(mm[i], f, slope, sle1);
+                v[18] = cur.hr ? norm_act<ACT>(cur.r.x, f, slope, sle1) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = b;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) a = fmaf(w[j], v[2 * i + j], a);
+                    o[i] = a;
+                }
+            }
+            float* yr = ys + (size_t)cur.c * Lout + 8 * cur.q;
+            st_stream4(yr, make_float4(o[0], o[1], o[2], o[3]));
+            st_stream4(yr + 4, make_float4(o[4], o[5], o[6], o[7]));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc_s += o[i]; acc_q = fmaf(o[i], o[i], acc_q); }
+        }
+        if (it + 1 < kDw8Items) cur = nxt;
+    }
+    block_stats_atomic(acc_s, acc_q, stats_out, sample, s_red);
+}
+#endif  // SDR_DW_PIPELINE
 
 // merge, 16 outputs per thread, coarse-to-fine: s_d[i] = z_d[i]*a_d + (b_d + s_{d+1}[i>>1])
 // requires depth >= 4 and L % 16 == 0
@@ -629,7 +756,11 @@ int launch_depthwise(const float* x, const NormIn& nin, const float* w5, const f
         const long long grid = (long long)chunks * samples;
         if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
         const bool act = nin.prelu != nullptr;
+#if SDR_DW_PIPELINE
+#define SDR_DW(S, A) dw5_wide_pipe_kernel<S, A><<<(unsigned)grid, kDw8Threads, 0, st>>>(x, nin, w5, bias, y, stats_out, C, Lin, Lout, chunks)
+#else
 #define SDR_DW(S, A) dw5_wide_kernel<S, A><<<(unsigned)grid, kDw8Threads, 0, st>>>(x, nin, w5, bias, y, stats_out, C, Lin, Lout, chunks)
+#endif
         if (stride == 1) { if (act) SDR_DW(1, true); else SDR_DW(1, false); }
         else             { if (act) SDR_DW(2, true); else SDR_DW(2, false); }
 #undef SDR_DW
