@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import warnings
 from typing import List
 
 import torch
@@ -16,6 +17,7 @@ import torch
 from . import _native as N
 
 _tls_lock = threading.Lock()
+_warned_detached = False
 
 
 def make_config(model) -> N.SdrConfig:
@@ -75,7 +77,8 @@ def _fetch(model, dotted: str) -> torch.Tensor:
 
 class _DeviceState:
     """Per (model, device) cache: packed weights + workspace."""
-    __slots__ = ("sig", "packed", "workspace", "staging", "tensors", "graphs")
+    __slots__ = ("sig", "packed", "workspace", "staging", "tensors", "pslots", "mslots", "graphs",
+                 "stream", "event")
 
     def __init__(self):
         self.sig = None
@@ -83,7 +86,11 @@ class _DeviceState:
         self.workspace = None
         self.staging = None
         self.tensors = None      # cached parameter tensors in state_dict order (never for DataParallel replicas)
+        self.pslots = None       # (leaf._parameters, key) per tensor: identity check without the attribute walk
+        self.mslots = None       # (parent._modules, name, child) per module on the way: catches replaced sub-modules
         self.graphs = {}         # forward_host: CUDA graphs keyed by (host buffers, shape, weights signature)
+        self.stream = None       # stream of the last enqueue on this workspace
+        self.event = None        # recorded after the last enqueue (cross-stream serialisation)
 
 
 def _state(model, device) -> _DeviceState:
@@ -97,28 +104,121 @@ def _state(model, device) -> _DeviceState:
     return st
 
 
+def drop_cache(model) -> None:
+    """Forget packed weights, workspaces and captured graphs (they are rebuilt on the next call)."""
+    model.__dict__.pop("_b200_cache", None)
+
+
+class NativeModuleMixin:
+    """Keeps the device-side cache (packed weights, a multi-GB workspace, CUDA graphs) out of pickles and
+    deep copies: ``torch.save(model)`` / ``copy.deepcopy(model)`` after a forward behave as for the reference."""
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_b200_cache", None)
+        return state
+
+
 def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _enter_stream(st: _DeviceState, device):
+    """One workspace per (model, device): a call arriving on a different stream than the previous one waits
+    for it (the scratch buffers are shared), and tells the caching allocator about the second stream."""
+    cur = torch.cuda.current_stream(device)
+    if torch.cuda.is_current_stream_capturing():     # the capturing caller owns the ordering
+        return cur
+    if st.stream is not None and st.stream != cur and st.event is not None:
+        cur.wait_event(st.event)
+        for buf in (st.workspace, st.staging, st.packed):
+            if buf is not None:
+                buf.record_stream(cur)
+    return cur
+
+
+def _leave_stream(st: _DeviceState, cur) -> None:
+    if torch.cuda.is_current_stream_capturing():
+        return
+    if st.event is None:
+        st.event = torch.cuda.Event()
+    st.event.record(cur)
+    st.stream = cur
+
+
+def _ensure_workspace(st: _DeviceState, nbytes: int, device) -> None:
+    if st.workspace is None or st.workspace.numel() < nbytes:
+        if st.event is not None:
+            st.event.synchronize()      # kernels of an earlier call (possibly on another stream) still use it
+        st.workspace = None
+        st.graphs.clear()               # captured graphs point into the old workspace
+        st.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def _walk(model, names):
+    """Attribute walk recording, besides the tensors, where each one hangs (for the cheap identity check)."""
+    tensors, pslots, mslots, seen = [], [], [], set()
+    for dotted in names:
+        obj = model
+        parts = dotted.split(".")
+        for part in parts[:-1]:
+            child = obj._modules[part]
+            key = (id(obj), part)
+            if key not in seen:
+                seen.add(key)
+                mslots.append((obj._modules, part, child))
+            obj = child
+        t = obj._parameters[parts[-1]]
+        tensors.append(t)
+        pslots.append((obj._parameters, parts[-1]))
+    return tensors, pslots, mslots
+
+
+def _cached_tensors(st: _DeviceState):
+    """The cached parameter list if every module and Parameter object on the way is still the same object."""
+    if st.tensors is None:
+        return None
+    try:
+        for d, k, child in st.mslots:
+            if d[k] is not child:
+                return None
+        for (d, k), t in zip(st.pslots, st.tensors):
+            if d[k] is not t:
+                return None
+    except KeyError:
+        return None
+    return st.tensors
+
+
 def packed_weights(model, cfg: N.SdrConfig, device) -> torch.Tensor:
-    """Flat packed-weight buffer for ``model`` on ``device`` (re-packed whenever a
-    parameter's storage or version counter changes)."""
+    """Flat packed-weight buffer for ``model`` on ``device``.
+
+    Master modules: re-packed whenever a parameter's storage or version counter changes, or a Parameter /
+    sub-module object was replaced (identity of every object on the path is checked, ~50 us).
+    ``nn.DataParallel`` replicas: packed on EVERY forward.  Their parameters are fresh broadcast copies whose
+    ``_version`` is always 0 and whose addresses the caching allocator reuses, so no signature can tell a new
+    set of weights from the previous one; the replica shares ``_b200_cache`` with its master."""
     lib = N.lib()
     st = _state(model, device)
+    replica = bool(getattr(model, "_is_replica", False))
     names = None
-    # The attribute walk over ~500 parameters costs ~0.7 ms; reuse the tensor objects of the previous call
-    # (in-place updates, .to()/.cuda() and load_state_dict keep the Parameter objects and are caught by the
-    # (data_ptr, _version) signature).  DataParallel replicas get fresh tensors every forward: never cached.
-    tensors = st.tensors if not getattr(model, "_is_replica", False) else None
-    if tensors is None or len(tensors) == 0 or tensors[0] is not _fetch(model, "encoder.weight") \
-            or tensors[-1] is not _fetch(model, "decoder.weight"):
+    if replica:
         names = state_dict_names(cfg)
         tensors = [_fetch(model, n) for n in names]
-        st.tensors = None if getattr(model, "_is_replica", False) else tensors
-    sig = tuple([(t.data_ptr(), t._version) for t in tensors])
-    if st.sig == sig and st.packed is not None:
-        return st.packed
+        sig = None
+    else:
+        tensors = _cached_tensors(st)
+        if tensors is None:
+            names = state_dict_names(cfg)
+            try:
+                tensors, st.pslots, st.mslots = _walk(model, names)
+                st.tensors = tensors
+            except KeyError:           # parameters held as plain attributes: no caching
+                tensors = [_fetch(model, n) for n in names]
+                st.tensors = st.pslots = st.mslots = None
+        sig = tuple([(t.data_ptr(), t._version) for t in tensors])
+        if st.sig == sig and st.packed is not None:
+            return st.packed
     if names is None:
         names = state_dict_names(cfg)
     n = lib.sdr_num_params(C.byref(cfg))
@@ -135,6 +235,8 @@ def packed_weights(model, cfg: N.SdrConfig, device) -> torch.Tensor:
             raise RuntimeError(f"parameter {name} has {t.numel()} elements, expected {want}")
         flat.append(t.detach().to(torch.float32).contiguous())
     nbytes = lib.sdr_packed_weight_bytes(C.byref(cfg))
+    # the master (and a replica on the master's device, which shares this state) may have graphs / in-flight
+    # kernels on the old buffer: always pack into a fresh one, the allocator recycles it stream-safely
     packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
     ptrs = (C.c_void_p * n)(*[C.c_void_p(t.data_ptr()) for t in flat])
     N.check(lib.sdr_pack_weights(C.byref(cfg), ptrs, n, C.c_void_p(packed.data_ptr()), nbytes,
@@ -161,6 +263,12 @@ def _check_input(model, cfg, wav: torch.Tensor) -> torch.Tensor:
             "model.eval() and/or wrap the call in torch.no_grad().")
     if wav.shape[0] == 0 or wav.shape[-1] == 0:
         raise RuntimeError("empty batch or zero-length mixture")
+    global _warned_detached
+    if torch.is_grad_enabled() and not _warned_detached and \
+            any(_fetch(model, n).requires_grad for n in ("encoder.weight", "decoder.weight")):
+        _warned_detached = True
+        warnings.warn("sudo_rm_rf_b200: the native forward is inference-only; the returned estimates are detached "
+                      "from autograd (wrap the call in torch.no_grad() to silence this).", stacklevel=3)
     # the reference casts to fp32 while padding (improved_sudormrf.py:312)
     return wav.detach().to(torch.float32).contiguous()
 
@@ -170,6 +278,9 @@ def forward(model, wav: torch.Tensor, mixture_consistency: bool = False) -> torc
     lib = N.lib()
     cfg = make_config(model)
     x = _check_input(model, cfg, wav)
+    if mixture_consistency and cfg.in_audio_channels != 1:
+        raise RuntimeError("mixture consistency (mixture_consistency.py:14-36) is defined for mono mixtures only; "
+                           f"this model has in_audio_channels={cfg.in_audio_channels}")
     device = x.device
     B, _, T = x.shape
     with torch.cuda.device(device):
@@ -178,16 +289,16 @@ def forward(model, wav: torch.Tensor, mixture_consistency: bool = False) -> torc
         ws_bytes = lib.sdr_workspace_bytes(C.byref(cfg), B, T)
         if ws_bytes == 0:
             raise N.NativeError("bad model configuration (sdr_workspace_bytes returned 0)")
-        if st.workspace is None or st.workspace.numel() < ws_bytes:
-            st.workspace = None
-            st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        _ensure_workspace(st, ws_bytes, device)
         out = torch.empty((B, cfg.num_sources * cfg.in_audio_channels, T),
                           dtype=torch.float32, device=device)
+        cur = _enter_stream(st, device)
         N.check(lib.sdr_forward(C.byref(cfg), C.c_void_p(packed.data_ptr()),
                                 C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
                                 B, T, 1 if mixture_consistency else 0,
                                 C.c_void_p(st.workspace.data_ptr()), st.workspace.numel(),
-                                _stream_ptr(device)), "sdr_forward")
+                                C.c_void_p(cur.cuda_stream)), "sdr_forward")
+        _leave_stream(st, cur)
     return out
 
 
@@ -212,16 +323,15 @@ def separate(model, wav: torch.Tensor, mixture_consistency: bool = False) -> tor
         ws_bytes = lib.sdr_separate_workspace_bytes(C.byref(cfg), B, T)
         if ws_bytes == 0:
             raise N.NativeError("bad model configuration (sdr_separate_workspace_bytes returned 0)")
-        if st.workspace is None or st.workspace.numel() < ws_bytes:
-            st.workspace = None
-            st.graphs.clear()
-            st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        _ensure_workspace(st, ws_bytes, device)
         out = torch.empty((B, cfg.num_sources, T), dtype=torch.float32, device=device)
+        cur = _enter_stream(st, device)
         N.check(lib.sdr_separate(C.byref(cfg), C.c_void_p(packed.data_ptr()),
                                  C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
                                  B, T, 1 if mixture_consistency else 0,
                                  C.c_void_p(st.workspace.data_ptr()), st.workspace.numel(),
-                                 _stream_ptr(device)), "sdr_separate")
+                                 C.c_void_p(cur.cuda_stream)), "sdr_separate")
+        _leave_stream(st, cur)
     return out
 
 
@@ -259,13 +369,13 @@ def forward_host(model, host_wav: torch.Tensor, host_out: torch.Tensor = None,
         io_bytes = lib.sdr_host_staging_bytes(C.byref(cfg), B, T)
         if ws_bytes == 0 or io_bytes == 0:
             raise N.NativeError("bad model configuration")
-        if st.workspace is None or st.workspace.numel() < ws_bytes:
-            st.workspace = None
-            st.graphs.clear()
-            st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        _ensure_workspace(st, ws_bytes, device)
         if st.staging is None or st.staging.numel() < io_bytes:
+            if st.event is not None:
+                st.event.synchronize()
             st.graphs.clear()
             st.staging = torch.empty(io_bytes, dtype=torch.uint8, device=device)
+        cur0 = _enter_stream(st, device)
 
         def enqueue():
             N.check(lib.sdr_forward_host(C.byref(cfg), C.c_void_p(packed.data_ptr()),
@@ -279,6 +389,7 @@ def forward_host(model, host_wav: torch.Tensor, host_out: torch.Tensor = None,
             and not torch.cuda.is_current_stream_capturing()
         if not graphable:
             enqueue()
+            _leave_stream(st, cur0)
             return host_out
         key = (host_wav.data_ptr(), host_out.data_ptr(), B, T, mc, st.workspace.data_ptr(),
                st.staging.data_ptr(), packed.data_ptr())
@@ -300,4 +411,5 @@ def forward_host(model, host_wav: torch.Tensor, host_out: torch.Tensor = None,
             graph.replay()
         else:
             entry.replay()
+        _leave_stream(st, cur0)
     return host_out

@@ -210,6 +210,9 @@ static Plan make_plan(const Layout& l, int B, long long T) {
 static int forward_impl(const Layout& l, const float* pk, const float* mixture, float* out,
                         int B, long long T, int apply_mc, char* ws, cudaStream_t st,
                         const float2* rescale = nullptr) {
+    // mixture_consistency.apply (mixture_consistency.py:14-36) sums the estimates over dim 1 and broadcasts against a
+    // [B, 1, T] mixture: it is only defined for mono models; refuse instead of silently skipping the projection
+    if (apply_mc && l.A != 1) return SDR_ERR_UNSUPPORTED;
     const Plan p = make_plan(l, B, T);
     const int L = p.L, D = l.D;
     double* stats = reinterpret_cast<double*>(ws + p.o_stats);
@@ -313,7 +316,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     // decoder: frames = Wd^T masked, then overlap-add / crop / mixture consistency
     SDR_TRY(pointwise(masked, none, pk + l.dec_wt, l.dec_pk ? pk + l.dec_pk : nullptr, nullptr, nullptr, nullptr, 0,
                       frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
-    const float* mix = (apply_mc && l.A == 1) ? mixture : nullptr;
+    const float* mix = apply_mc ? mixture : nullptr;
     SDR_TRY(launch_overlap_add(frames, mix, rescale, out, B, l.S * l.A, l.K, L, T, st));
     return SDR_OK;
 }

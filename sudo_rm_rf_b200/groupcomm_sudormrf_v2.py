@@ -43,7 +43,7 @@ class GC_UConvBlock(nn.Module):
     forward = _not_standalone
 
 
-class GroupCommSudoRmRf(nn.Module):
+class GroupCommSudoRmRf(_engine.NativeModuleMixin, nn.Module):
     """Group-communication SuDoRM-RF (reference :231-339) on the B200 native path."""
 
     def __init__(self, in_audio_channels=1, out_channels=256, in_channels=512, num_blocks=16,

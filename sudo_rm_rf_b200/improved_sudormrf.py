@@ -106,7 +106,7 @@ def _xavier_uniform_(w):
         w.uniform_(-bound, bound)
 
 
-class SuDORMRF(nn.Module):
+class SuDORMRF(_engine.NativeModuleMixin, nn.Module):
     """Improved SuDoRM-RF separator (reference :223-318) on the B200 native path."""
 
     def __init__(self, out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
