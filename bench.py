@@ -145,45 +145,67 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle port of the reference forward
 # --------------------------------------------------------------------------
+def host_cores():
+    """(logical CPUs visible to this process, physical cores)."""
+    logical = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or logical
+    except Exception:
+        physical = logical
+    return logical, physical
+
+
 def cpu_forward_rate(w, sample_B, steps, warmup, budget_s=None):
-    """mixtures/s of the CPU oracle port (same torch op sequence as the reference's
-    forward, improved_sudormrf.py:283-301) on all host cores."""
+    """mixtures/s of the CPU oracle port (same torch op sequence as the reference's forward,
+    improved_sudormrf.py:283-301) on ALL host cores.  Protocol of BASELINE.md section 2 / the reference's notebook
+    (sudormrf_extract_computation_metrics_example.ipynb:125-146): batch 1, >= 10 repetitions, median.
+    torchrun exports OMP_NUM_THREADS=1 per rank, so the thread count is set explicitly."""
     from oracle import sudormrf_oracle as O
+    logical, physical = host_cores()
+    # one thread per PHYSICAL core: with one per logical CPU (SMT) the GlobLN passes of the port ran 40x slower
+    # on the 64-core / 128-thread box (80 s per forward instead of ~0.3-0.6 s)
+    torch.set_num_threads(max(1, min(logical, physical)))
     cfg = O.Config(variant=w["variant"], **w["kw"])
     sd = O.make_state_dict(cfg, seed=0, perturbed=False)
     x = torch.rand(sample_B, 1, w["T"], generator=torch.Generator().manual_seed(1))
+    times = []
     with torch.no_grad():
         for _ in range(warmup):
             O.forward(cfg, sd, x)
-        t0 = time.perf_counter()
-        done = 0
+        t_start = time.perf_counter()
         for _ in range(steps):
+            t0 = time.perf_counter()
             O.forward(cfg, sd, x)
-            done += 1
-            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            times.append(time.perf_counter() - t0)
+            if budget_s is not None and time.perf_counter() - t_start > budget_s and len(times) >= 3:
                 break
-        dt = time.perf_counter() - t0
-    return sample_B * done / dt, dt / done, done
+    times.sort()
+    med = times[len(times) // 2]
+    return {"rate": sample_B / med, "sec_per_step": med, "done": len(times), "threads": torch.get_num_threads(),
+            "logical_cpus": logical, "physical_cores": physical, "best": sample_B / times[0]}
 
 
 def run_reference(args, w, wl_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = 2
-    cores = torch.get_num_threads()
-    rate, sec_per_step, done = cpu_forward_rate(w, sample_B, args.steps, args.warmup)
+    sample_B = 1
+    r = cpu_forward_rate(w, sample_B, max(args.steps, 10), max(args.warmup, 1), budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": done, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+        "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["done"], "warmup": max(args.warmup, 1), "ms_per_step": r["sec_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (torch.rand mixtures, default-init weights)",
         "config": {"workload": wl_name, "batch_per_step": sample_B, "samples": w["T"],
-                   "note": "CPU oracle port of the reference forward (the Python reference cannot "
-                           "travel to the GPU box); bounded sample of the workload per step"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{done} forwards of batch {sample_B} x {w['T']} samples"},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   "note": "CPU arm = this repo's oracle PORT of the reference forward (oracle/sudormrf_oracle.py: the same "
+                           "torch op sequence, pinned bit-exactly to reference-generated goldens); it is NOT the unmodified "
+                           "reference module, which is not shipped to the GPU box.  Batch 1, median over the steps, all host "
+                           "cores (BASELINE.md section 2 protocol); under torchrun only rank 0 runs."},
+        "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["threads"], "physical_cores": r["physical_cores"],
+                         "kind": "port", "best": r["best"],
+                         "sample": f"median of {r['done']} forwards of batch {sample_B} x {w['T']} samples"},
+        "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -279,15 +301,28 @@ def run_b200(args, w, wl_name):
         barrier()
         e2e_ms = e0.elapsed_time(e1)
 
-        # ---- dominant kernel, timed alone with CUDA events on the launching stream ----
+        # ---- every kernel of a U-ConvBlock alone + the block as a whole (CUDA events on the launching stream) ----
         roof = None
+        lat1 = None
         if rank == 0:
-            roof = time_dominant_kernel(w, B, stream, flush, dev)
+            roof = roofline_block(w, B, stream, flush, dev)
+            lat1 = latency_b1(model, w, dev, stream)
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # ---- the other BASELINE configs, short runs on every rank (so the 8-GPU scaling run yields their figures too) ----
+    others = []
+    other_ms = []
+    if wl_name == "improved_u16_512" and not args.no_other_configs:
+        del graph
+        torch.cuda.empty_cache()
+        for name in ("improved_u36_2048", "groupcomm_u8_512", "improved_u36_4096_16k"):
+            ow, ms, n_par = short_config_run(name, dev, stream, flush)
+            others.append((name, ow, n_par))
+            other_ms.append(ms)
+
+    t = torch.tensor([dev_ms, e2e_ms] + other_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, *other_ms = t.tolist()
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -297,12 +332,24 @@ def run_b200(args, w, wl_name):
         value = total_mix / (dev_ms / 1e3)
         fwd_bytes = B * am["a_mix"] + 4 * n_params
         fwd_gbs = fwd_bytes / (dev_ms / args.steps / 1e3) / 1e9
-        if world == 1:      # the CPU leg is timed at N=1 only (torchrun pins OMP threads to 1 per rank)
-            cpu_rate, cpu_sec, cpu_done = cpu_forward_rate(w, 2, steps=64, warmup=1, budget_s=12.0)
-            cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": f"{cpu_done} forwards of batch 2 x {T} samples ({cpu_sec:.2f} s each), same model"}
+        eager = None
+        if world == 1:      # comparators are timed at N=1 only
+            eager = eager_cuda_rate(w, B, dev)
+            r = cpu_forward_rate(w, 1, steps=30, warmup=1, budget_s=15.0)
+            cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": r["threads"], "physical_cores": r["physical_cores"],
+                            "kind": "port", "best": r["best"],
+                            "sample": f"median of {r['done']} forwards of batch 1 x {T} samples "
+                                      f"({r['sec_per_step']:.2f} s each), same model, oracle port of the reference forward"}
         else:
             cpu_baseline = None
+        other_configs = []
+        for (name, ow, n_par), ms in zip(others, other_ms):
+            oam = algorithmic_model(ow)
+            ob = ow["B"] * oam["a_mix"] + 4 * n_par
+            other_configs.append({"workload": name, "batch_per_gpu": ow["B"], "global_batch": ow["B"] * world,
+                                  "samples": ow["T"], "steps": 5, "ms_per_step": ms,
+                                  "value": ow["B"] * world / (ms / 1e3), "unit": UNIT,
+                                  "forward_hbm_frac": ob / (ms / 1e3) / 1e9 / peak})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -326,6 +373,9 @@ def run_b200(args, w, wl_name):
                             "unit": "GB/s", "frac": fwd_gbs / peak, "peak_source": peak_src,
                             "gflop_per_mixture": am["flops"] / 1e9},
             "cpu_baseline": cpu_baseline,
+            "eager_cuda_baseline": eager,
+            "other_configs": other_configs,
+            "latency_b1": lat1,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -333,76 +383,246 @@ def run_b200(args, w, wl_name):
         dist.destroy_process_group()
 
 
-def time_dominant_kernel(w, B, stream, flush, dev):
-    """The dominant kernel of the step is the res_conv pointwise GEMM (+skip) of the
-    U-ConvBlocks: time it alone at the benchmark shape with CUDA events."""
+# --------------------------------------------------------------------------
+# per-kernel and per-U-ConvBlock timing through the stage-level C-ABI entry points
+# --------------------------------------------------------------------------
+def block_launchers(w, B, dev, stream):
+    """The 3 + D kernels of ONE U-ConvBlock at the workload's shapes, in forward order, as
+    [(name, launch, algorithmic_bytes, flops)], operating on synthetic tensors through the stage-level C-ABI
+    (the same entry points `sdr_forward` dispatches to).  Returns (launchers, keepalive)."""
     import ctypes as C
     from sudo_rm_rf_b200 import _native as N
+    lib = N.lib()
     kw = w["kw"]
     gc = w["variant"] == "groupcomm"
     G = kw.get("group_size", 1) if gc else 1
     am = algorithmic_model(w)
-    L = am["L"]
-    samples, M, K = B * G, kw["out_channels"] // G, kw["in_channels"] // G
-    gen = torch.Generator(device=dev).manual_seed(0)
-    xin = torch.randn(samples, K, L, device=dev, generator=gen)
-    Wt = torch.randn(M, K, device=dev, generator=gen) / K ** 0.5
-    bias = torch.randn(M, device=dev, generator=gen)
-    gamma = torch.ones(K, device=dev)
-    beta = torch.zeros(K, device=dev)
-    slope = torch.full((1,), 0.25, device=dev)
-    xd = xin.double().reshape(samples, -1)
-    stats = torch.stack([xd.sum(1), (xd * xd).sum(1)], 1).contiguous()
-    res = torch.randn(samples, M, L, device=dev, generator=gen)
-    nin = N.SdrNormIn(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), slope.data_ptr(), float(K * L))
+    L, D = am["L"], kw["upsampling_depth"]
+    S, Co, Ci = B * G, kw["out_channels"] // G, kw["in_channels"] // G
     sp = C.c_void_p(stream.cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *shape: torch.randn(*shape, device=dev, generator=gen)
+    ones, zeros = torch.ones(max(Ci, Co), device=dev), torch.zeros(max(Ci, Co), device=dev)
+    slope = torch.full((1,), 0.25, device=dev)
+    keep = [ones, zeros, slope]
 
-    nbytes = N.lib().sdr_pointwise_mma_packed_bytes(M, K)
-    wpk = None
-    if nbytes:
-        wpk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        N.check(N.lib().sdr_pointwise_mma_pack(C.c_void_p(Wt.data_ptr()), M, K, C.c_void_p(wpk.data_ptr()), sp))
+    def stats_of(t):
+        td = t.double().reshape(t.shape[0], -1)
+        return torch.stack([td.sum(1), (td * td).sum(1)], 1).contiguous()
 
-    def launch():
-        if wpk is not None:       # the path the forward takes for this shape (tcgen05)
-            N.check(N.lib().sdr_pointwise_mma(
-                C.c_void_p(xin.data_ptr()), C.byref(nin), C.c_void_p(wpk.data_ptr()),
-                C.c_void_p(bias.data_ptr()), C.c_void_p(res.data_ptr()), C.c_void_p(0), 0,
-                C.c_void_p(res.data_ptr()), C.c_void_p(0), samples, M, K, L, 0, sp))
-        else:
-            N.check(N.lib().sdr_pointwise(
-                C.c_void_p(xin.data_ptr()), C.byref(nin), C.c_void_p(Wt.data_ptr()),
-                C.c_void_p(bias.data_ptr()), C.c_void_p(res.data_ptr()), C.c_void_p(0), 0,
-                C.c_void_p(res.data_ptr()), C.c_void_p(0), samples, M, K, L, 0, sp))
+    x = rn(S, Co, L)                      # block input == residual stream (updated in place by res_conv)
+    y = torch.empty(S, Ci, L, device=dev)
+    z = [torch.empty(S, Ci, L >> d, device=dev) for d in range(D)]
+    st = [torch.zeros(S, 2, dtype=torch.float64, device=dev) for _ in range(D + 2)]
+    keep += [x, y, z, st]
+    out = []
 
-    for _ in range(3):
-        launch()
-    reps = 10
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for s, e in evs:
-        flush.fill_(2)
-        s.record(stream)
-        launch()
-        e.record(stream)
-    stream.synchronize()
-    ms = sorted(s.elapsed_time(e) for s, e in evs)
-    avg = sum(ms) / len(ms)
+    def gemm(name, xin, nin, M, K, res, yout, stats):
+        Wt = rn(M, K) / K ** 0.5
+        bias = rn(M)
+        nbytes = lib.sdr_pointwise_mma_packed_bytes(M, K)
+        keep.extend([Wt, bias])
+        if nbytes:
+            wpk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            N.check(lib.sdr_pointwise_mma_pack(P(Wt), M, K, P(wpk), sp))
+            keep.append(wpk)
+            fn = lambda: N.check(lib.sdr_pointwise_mma(P(xin), C.byref(nin), P(wpk), P(bias), P(res), P(None), 0,
+                                                       P(yout), P(stats), S, M, K, L, 0, sp))
+            return name + " [pw_mma_kernel tcgen05 bf16x3]", fn
+        fn = lambda: N.check(lib.sdr_pointwise(P(xin), C.byref(nin), P(Wt), P(bias), P(res), P(None), 0,
+                                               P(yout), P(stats), S, M, K, L, 0, sp))
+        return name + " [pw_gemm_kernel FFMA]", fn
+
+    # proj_1x1: raw residual stream in, raw y + statistics out
+    none = N.SdrNormIn(0, 0, 0, 0, 1.0)
+    keep.append(none)
+    n_, f_ = gemm("proj_1x1", x, none, Ci, Co, None, y, st[0])
+    out.append((n_, f_, 4 * L * S * (Co + Ci), 2.0 * Co * Ci * L * S))
+    # depthwise levels (producer's GlobLN (+PReLU for level 0) applied on load)
+    for d in range(D):
+        src = y if d == 0 else z[d - 1]
+        Lin = L if d == 0 else L >> (d - 1)
+        nin = N.SdrNormIn(st[d].data_ptr(), ones.data_ptr(), zeros.data_ptr(), slope.data_ptr() if d == 0 else 0,
+                          float(Ci * Lin))
+        w5, b5 = rn(Ci, 5), rn(Ci)
+        keep.extend([nin, w5, b5])
+        stride = 1 if d == 0 else 2
+        out.append((f"depthwise level {d} (stride {stride})",
+                    (lambda src=src, nin=nin, w5=w5, b5=b5, d=d, Lin=Lin, stride=stride: N.check(lib.sdr_depthwise(
+                        P(src), C.byref(nin), P(w5), P(b5), P(z[d]), P(st[d + 1]), S, Ci, Lin, stride, sp))),
+                    4 * S * Ci * (Lin + (L >> d)), 10.0 * Ci * (L >> d) * S))
+    # merge (m reuses y's storage, as in the forward)
+    fins = (N.SdrNormIn * D)(*[N.SdrNormIn(st[d + 1].data_ptr(), ones.data_ptr(), zeros.data_ptr(), 0,
+                                           float(Ci * (L >> d))) for d in range(D)])
+    zp = (C.c_void_p * D)(*[t.data_ptr() for t in z])
+    keep.extend([fins, zp])
+    out.append(("merge", lambda: N.check(lib.sdr_merge(zp, fins, D, P(y), P(st[D + 1]), S, Ci, L, sp)),
+                4 * S * Ci * (L + sum(L >> d for d in range(D))), 3.0 * D * Ci * L * S))
+    # res_conv + in-place skip connection
+    nf = N.SdrNormIn(st[D + 1].data_ptr(), ones.data_ptr(), zeros.data_ptr(), slope.data_ptr(), float(Ci * L))
+    keep.append(nf)
+    n_, f_ = gemm("res_conv+skip", y, nf, Co, Ci, x, x, None)
+    out.append((n_, f_, 4 * L * S * (Ci + 2 * Co), 2.0 * Co * Ci * L * S))
+
+    def reset():
+        for t in st:
+            t.zero_()
+    return out, reset, keep
+
+
+def time_block(w, B, stream, flush, dev, reps=7):
+    """Times every kernel of one U-ConvBlock alone (L2 flushed before each launch) and the block as a whole
+    (its kernels back to back as in the forward, L2 flushed before the block only).  CUDA events on the
+    launching stream; medians."""
     peak, peak_src = load_peaks()
-    traffic = None      # dram__bytes_read+write per launch of this kernel at this shape, from the committed ncu capture
+    am = algorithmic_model(w)
+    launchers, reset, keep = block_launchers(w, B, dev, stream)
+
+    def med(fn, n=reps):
+        ms = []
+        for _ in range(n):
+            reset()
+            flush.fill_(3)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            fn()
+            e.record(stream)
+            stream.synchronize()
+            ms.append(s.elapsed_time(e))
+        ms.sort()
+        return ms[len(ms) // 2]
+
+    def whole():
+        for _, fn, _, _ in launchers:
+            fn()
+    for _ in range(2):
+        reset()
+        whole()
+    stream.synchronize()
+    kernels = []
+    for name, fn, nbytes, flops in launchers:
+        t = med(fn)
+        kernels.append({"kernel": name, "avg_launch_ms": t, "algorithmic_bytes_per_launch": nbytes,
+                        "achieved": nbytes / t / 1e6, "frac": nbytes / t / 1e6 / peak,
+                        "tflops_fp32_equivalent": flops / t / 1e9})
+    t_blk = med(whole)
+    gc = w["variant"] == "groupcomm"
+    blk_bytes = B * (am["a_blk"] - (4 * am["L"] * 4 * w["kw"]["out_channels"] if gc else 0))   # TAC is not in this sequence
+    per_block = {"ms": t_blk, "sum_of_kernels_ms": sum(k["avg_launch_ms"] for k in kernels),
+                 "algorithmic_bytes": blk_bytes, "achieved": blk_bytes / t_blk / 1e6, "peak": peak, "unit": "GB/s",
+                 "frac": blk_bytes / t_blk / 1e6 / peak,
+                 "what": "proj_1x1 -> depthwise levels -> merge -> res_conv+skip of one U-ConvBlock at the benchmark shape, "
+                         "launched back to back through the stage-level C-ABI (L2 flushed before the block)"}
+    del keep
+    return kernels, per_block, peak, peak_src
+
+
+def roofline_block(w, B, stream, flush, dev):
+    """`roofline` = the kernel with the largest share of the step (chosen from the measured per-kernel times, not
+    assumed), next to every other kernel of the U-ConvBlock and the per-U-ConvBlock figure the north star names."""
+    kernels, per_block, peak, peak_src = time_block(w, B, stream, flush, dev)
+    top = max(kernels, key=lambda k: k["avg_launch_ms"])
+    traffic = None      # dram__bytes_read+write per launch of that kernel at this shape, from the committed ncu capture
     tpath = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
-        if t.get("shape") == {"samples": samples, "M": M, "K": K, "L": L}:
-            traffic = t.get("dram_bytes_per_launch")
-    bytes_per_launch = B * am["res_bytes"]
-    achieved = bytes_per_launch / (avg / 1e3) / 1e9
-    return {"kernel": "pointwise GEMM res_conv+skip (" + ("pw_mma_kernel, tcgen05 bf16x3" if wpk is not None else "pw_gemm_kernel, FFMA") + ")",
-            "bound": "hbm",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg,
-            "tflops_fp32_equivalent": B * am["res_flops"] / (avg / 1e3) / 1e12,
-            "shape": {"samples": samples, "M": M, "K": K, "L": L}}
+        for ent in (t if isinstance(t, list) else [t]):
+            if ent.get("kernel_prefix") and top["kernel"].startswith(ent["kernel_prefix"]) and \
+                    ent.get("algorithmic_bytes_per_launch") == top["algorithmic_bytes_per_launch"]:
+                traffic = ent.get("dram_bytes_per_launch")
+    return {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "avg_launch_ms": top["avg_launch_ms"],
+            "selection": "largest measured per-launch time among the U-ConvBlock's kernels (16 launches of each per step)",
+            "kernels": kernels, "per_block": per_block}
+
+
+# --------------------------------------------------------------------------
+# comparators next to the headline
+# --------------------------------------------------------------------------
+def eager_cuda_rate(w, B, dev, steps=5, warmup=2):
+    """The reference's op sequence run by stock PyTorch eager kernels (ATen / cuDNN / cuBLAS) on this GPU: the
+    oracle port on `cuda` (improved_sudormrf.py:283-301 under the notebook's timing protocol, :125-146).  This is the
+    "existing Blackwell path" a user of the reference gets today; fp32, TF32 state recorded."""
+    from oracle import sudormrf_oracle as O
+    cfg = O.Config(variant=w["variant"], **w["kw"])
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=0, perturbed=False).items()}
+    x = torch.rand(B, 1, w["T"], generator=torch.Generator().manual_seed(1)).to(dev)
+    ms = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.forward(cfg, sd, x)
+        torch.cuda.synchronize(dev)
+        for _ in range(steps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            O.forward(cfg, sd, x)
+            e.record()
+            torch.cuda.synchronize(dev)
+            ms.append(s.elapsed_time(e))
+    ms.sort()
+    med = ms[len(ms) // 2]
+    del sd, x
+    torch.cuda.empty_cache()
+    return {"value": B / (med / 1e3), "unit": UNIT, "ms_per_step": med, "batch": B, "steps": steps,
+            "what": "oracle port of the reference forward executed by stock torch eager CUDA kernels on this GPU",
+            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+            "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32), "dtype": "f32"}
+
+
+def short_config_run(name, dev, stream, flush, steps=5, warmup=3):
+    """A short device-resident run of another BASELINE config on this rank (same protocol as the headline)."""
+    import sudo_rm_rf_b200 as P
+    from oracle import sudormrf_oracle as O
+    w = WORKLOADS[name]
+    cls = P.SuDORMRF if w["variant"] == "improved" else P.GroupCommSudoRmRf
+    model = cls(**w["kw"])
+    model.load_state_dict(O.make_state_dict(O.Config(variant=w["variant"], **w["kw"]), seed=0, perturbed=False))
+    model = model.to(dev).eval()
+    x = torch.rand(w["B"], 1, w["T"], generator=torch.Generator().manual_seed(7)).to(dev)
+    with torch.no_grad(), torch.cuda.stream(stream):
+        model(x)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            model(x)
+        for _ in range(warmup):
+            graph.replay()
+        stream.synchronize()
+        tot = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            graph.replay()
+            e.record(stream)
+            stream.synchronize()
+            tot += s.elapsed_time(e)
+    n_params = sum(p.numel() for p in model.parameters())
+    del graph, model, x
+    torch.cuda.empty_cache()
+    return w, tot / steps, n_params
+
+
+def latency_b1(model, w, dev, stream, reps=20):
+    """Batch-1 latency through the public host-buffer API (pinned in/out, CUDA-graph replay, sync per call):
+    the protocol the reference publishes its GPU number with (B=1, notebook :125-146)."""
+    hx = torch.rand(1, 1, w["T"]).pin_memory()
+    hy = torch.empty(1, w["kw"]["num_sources"], w["T"]).pin_memory()
+    with torch.no_grad(), torch.cuda.stream(stream):
+        for _ in range(3):
+            model.forward_host(hx, hy)
+            stream.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            model.forward_host(hx, hy)
+            stream.synchronize()
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return {"ms": ts[len(ts) // 2] * 1e3, "best_ms": ts[0] * 1e3, "mixtures_per_s": 1.0 / ts[len(ts) // 2],
+            "api": "model.forward_host, batch 1, host wall clock incl. H2D + D2H + sync", "reps": reps}
 
 
 def main():
@@ -413,6 +633,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="improved_u16_512", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE configs 3 / 4 / 5")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

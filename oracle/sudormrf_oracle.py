@@ -204,7 +204,7 @@ def pad_wave(cfg: Config, wav: Tensor, dtype) -> Tensor:
     the reference materialises the pad in fp32."""
     T = wav.shape[-1]
     Tp = padded_length(cfg, T)
-    out = torch.zeros(list(wav.shape[:-1]) + [Tp], dtype=dtype)
+    out = torch.zeros(list(wav.shape[:-1]) + [Tp], dtype=dtype, device=wav.device)
     out[..., :T] = wav.to(dtype)
     return out
 
@@ -300,7 +300,7 @@ def forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor,
     """
     if wav.dim() != 3:
         raise RuntimeError("expected a 3-D input [batch, audio_channels, time]")
-    sd = {k: v.to(dtype) for k, v in sd.items()}
+    sd = {k: v.to(device=wav.device, dtype=dtype) for k, v in sd.items()}   # (bench.py times this op sequence on cuda too)
     T = wav.shape[-1]
     k, hop = cfg.enc_kernel_size, cfg.hop
     S, N = cfg.num_sources, cfg.enc_num_basis

@@ -20,11 +20,6 @@ int launch_overlap_add(const float*, const float*, const float2*, float*, int, i
 int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
-#if SDR_DW_CHAIN
-int launch_depthwise_chain(const float* const*, float* const*, const double* const*, double* const*, const float* const*,
-                           const float* const*, const float* const*, const float* const*, const int*, int, int, int, int,
-                           int*, cudaStream_t);
-#endif
 // pre/post steps (prepost.cu)
 int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
 int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
@@ -171,9 +166,6 @@ __global__ void transpose_decoder_kernel(const float* __restrict__ w, float* __r
 struct Plan {
     long long Tp; int L; int samples;          // samples = B (improved) or B*G
     int slots; size_t stats_doubles;
-#if SDR_DW_CHAIN
-    size_t chain_ints, o_chain;                // per block: work counter + per-(level, sample) completion counters
-#endif
     size_t o_stats, o_e, o_x, o_xt, o_o, o_y, o_z[kMaxDepthApi], o_masked, o_frames, total;  // bytes
 };
 
@@ -187,13 +179,7 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     size_t cur = 0;
     auto seg = [&](size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~(size_t)255; return o; };
     const size_t BL = (size_t)B * p.L * sizeof(float);
-#if SDR_DW_CHAIN
-    p.chain_ints = (size_t)l.U * (1 + (size_t)kMaxDepthApi * p.samples);
-    p.o_stats = seg(p.stats_doubles * sizeof(double) + p.chain_ints * sizeof(int));   // zeroed by the same memset
-    p.o_chain = p.o_stats + p.stats_doubles * sizeof(double);
-#else
     p.o_stats = seg(p.stats_doubles * sizeof(double));
-#endif
     p.o_e = seg(BL * l.N);
     p.o_x = seg(BL * l.Co);
     p.o_xt = l.gc ? seg(BL * l.Co) : 0;
@@ -228,12 +214,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     auto slot = [&](int s) { return stats + (size_t)s * p.samples * 2; };
     const NormIn none{nullptr, nullptr, nullptr, nullptr, 1.0};
 
-#if SDR_DW_CHAIN
-    if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double) + p.chain_ints * sizeof(int), st) != cudaSuccess)
-        return SDR_ERR_CUDA;
-#else
     if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
-#endif
 
     // front end: encoder (+stats), ln folded into the bottleneck's operand load
     if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, slot(0), B, l.A, T, l.N, l.K, L, st));
@@ -267,24 +248,6 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
             NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)cib * L};
             SDR_TRY(launch_depthwise(y, n0, pk + u.dw_w[0], pk + u.dw_b[0], z[0], slot(s0 + 1), ns, cib, L, 1, st));
         }
-#if SDR_DW_CHAIN
-        int chained = SDR_ERR_UNSUPPORTED;
-        if (D > 1) {                                // all stride-2 levels of this block in one persistent kernel
-            const float* cx[kMaxDepthApi]; float* cy[kMaxDepthApi];
-            const double* csi[kMaxDepthApi]; double* cso[kMaxDepthApi];
-            const float *cg[kMaxDepthApi], *cb[kMaxDepthApi], *cw[kMaxDepthApi], *cbi[kMaxDepthApi];
-            int cl[kMaxDepthApi];
-            for (int d = 1; d < D; ++d) {
-                cx[d] = z[d - 1]; cy[d] = z[d]; csi[d] = slot(s0 + d); cso[d] = slot(s0 + 1 + d);
-                cg[d] = pk + u.dw_g[d - 1]; cb[d] = pk + u.dw_be[d - 1]; cw[d] = pk + u.dw_w[d]; cbi[d] = pk + u.dw_b[d];
-                cl[d] = L >> (d - 1);
-            }
-            int* counters = reinterpret_cast<int*>(ws + p.o_chain) + (size_t)i * (1 + (size_t)kMaxDepthApi * ns);
-            chained = launch_depthwise_chain(cx, cy, csi, cso, cg, cb, cw, cbi, cl, 1, D - 1, ns, cib, counters, st);
-            if (chained != SDR_OK && chained != SDR_ERR_UNSUPPORTED) return chained;
-        }
-        if (chained != SDR_OK)
-#endif
         for (int d = 1; d < D; ++d) {
             NormIn nd{slot(s0 + d), pk + u.dw_g[d - 1], pk + u.dw_be[d - 1], nullptr, (double)cib * (L >> (d - 1))};
             SDR_TRY(launch_depthwise(z[d - 1], nd, pk + u.dw_w[d], pk + u.dw_b[d], z[d], slot(s0 + 1 + d),

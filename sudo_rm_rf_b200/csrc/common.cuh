@@ -4,10 +4,6 @@
 #include <stdint.h>
 #include "../../include/sudormrf_b200.h"
 
-#ifndef SDR_DW_CHAIN
-#define SDR_DW_CHAIN 0     // experiment switch (levels.cu, api.cu): stride-2 depthwise levels of a block in one persistent kernel
-#endif
-
 namespace sdr {
 
 constexpr int kMaxDepthApi = 8;   // deepest upsampling_depth the kernels take

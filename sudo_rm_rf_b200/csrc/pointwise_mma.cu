@@ -19,43 +19,41 @@
 //
 // Replaces (reference file:line): bottleneck improved_sudormrf.py:256-259,292;
 // proj_1x1.conv :174,205; res_conv(+skip) :196,220; mask_net :268-269,295-298.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace sdr {
 
-// L2 prefetch distance of the activation tiles, in k-blocks (swept: 2 -> 109 us, 4 -> 116 us, 8 -> 124 us on res_conv)
-constexpr int kTileM = 128;            // positions per tile (UMMA M, TMEM lanes)
+// CTA pairs (tcgen05 cta_group::2).  The kernel is launched as clusters of two CTAs (one TPC).  A pair works on one
+// (256 positions x tile_n channels) tile at a time: each CTA transforms ITS 128 positions into its own A stage and
+// loads only ITS half of the weight rows (tile_n / 2) into its own B stage; the leader CTA (cluster rank 0) issues
+// ONE UMMA (M = 256) per k-step for the pair, and each CTA's TMEM receives the accumulator rows of its own positions.
+// Why: with one CTA per tile the weight image (bf16 hi + lo = 4 B per weight) was re-streamed from L2 for every
+// 128-position tile -- 256 KB of weights against 128 KB of activations per proj tile -- and the main loop ran at the
+// L2 fabric limit (proj / mask with the epilogue disabled: 614 MB / 69.6 us and 1.23 GB / 140 us = 8.8 TB/s both,
+// profiles/r01d_tma_epilogue.md).  Pairing halves the weight traffic per position and frees 64 KB of shared memory
+// for a third pipeline stage.
+constexpr int kTileM = 128;            // positions per CTA tile (UMMA M per CTA, TMEM lanes)
 constexpr int kBlockK = 64;            // channels per k-block = one 128 B swizzle row of bf16
-constexpr int kAStages = 2;            // A (activation) and B (weight) stages share one full/empty barrier ring:
-constexpr int kBStages = 2;            // a tcgen05.commit per ring and k-block measured ~40 % slower than one
-static_assert(kAStages == kBStages, "one barrier ring");
-constexpr int kMaxTileN = 256;         // output channels per tile (UMMA N, TMEM columns per stage)
+constexpr int kStages = 3;             // A (activation) and B (weight) stages share one full/empty barrier ring
+constexpr int kMaxTileN = 256;         // output channels per tile (UMMA N, TMEM columns per accumulator stage)
 constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
-constexpr int kBHalfMax = kMaxTileN * 128;
+constexpr int kBHalfMax = (kMaxTileN / 2) * 128;             // 16 KB: this CTA's tile_n / 2 weight rows, one bf16 image
 constexpr int kAStageBytes = 2 * kAHalf;                     // 32 KB: hi + lo
-constexpr int kBStageBytes = 2 * kBHalfMax;                  // 64 KB: hi + lo
-#ifndef SDR_MMA_LEAN_PRODUCER
-#define SDR_MMA_LEAN_PRODUCER 0         // 1: transform loop with pointer-bumped cursors and the (scale, shift) table read before
-#endif                                  // the stage wait (round-2 experiment from the ncu source view; compiled, NOT measured yet)
-#ifndef SDR_MMA_EPI_WARPS
-#define SDR_MMA_EPI_WARPS 4             // epilogue warps of the plain-store exit (MODE 0).  8 = two per TMEM lane quarter, each
-#endif                                  // owning half of the tile's columns: a round-2 experiment, compiled but NOT measured yet
-#if SDR_MMA_EPI_WARPS == 4
+constexpr int kBStageBytes = 2 * kBHalfMax;                  // 32 KB: hi + lo
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
 #define SDR_MMA_THREADS(MODE) kMmaThreads
-#else
-static_assert(SDR_MMA_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
-constexpr int kEpiWarps = 4, kProdWarps = 8;                  // kEpiWarps: the staged exits and the shared-memory carve-up
-// warp roles: [0, EW) epilogue, EW MMA issuer, EW + 1 weight TMA, [EW + 2, EW + 10) operand transform
-constexpr int mma_epi_warps(int mode) { return mode == 0 ? SDR_MMA_EPI_WARPS : kEpiWarps; }
-constexpr int mma_threads(int mode) { return 32 * (mma_epi_warps(mode) + 2 + kProdWarps); }   // 448 or 576
-#define SDR_MMA_THREADS(MODE) mma_threads(MODE)
-#endif
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
+#ifndef SDR_MMA_LEAN_PRODUCER
+#define SDR_MMA_LEAN_PRODUCER 1         // transform loop with pointer-bumped cursors and the (scale, shift) table read before the
+#endif                                  // stage wait (round-2 A/B on the B200: res_conv 90 -> 82 us, bottleneck 84 -> 78 us)
 #ifndef SDR_MMA_BULK
 #define SDR_MMA_BULK 1                  // 1: the in-place skip connection (mode 3) leaves through staging tiles + TMA reduce-add
 #endif
@@ -76,7 +74,9 @@ struct MmaArgs {
     float* y;
     double* stats_out;
     int M, K, L;
-    int l_tiles, n_tiles, tile_n, num_tiles;
+    int l_tiles, n_tiles, tile_n;
+    int pos_tiles;        // samples * l_tiles: 128-position tiles, CTA `rank` of a pair takes tile 2 * pp + rank
+    int num_tiles;        // pair tiles = n_tiles * ceil(pos_tiles / 2)
     int epilogue;
     // window mode (encoder Conv1d as a GEMM without im2col): operand element (position p, k = a*win_k + j)
     // is wav[sample, a, win_hop * p + j - win_pad] (zero outside [0, win_T)); x = wav, K = padded taps
@@ -144,22 +144,77 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// TMEM of a CTA pair: one warp of EACH CTA issues the cta_group::2 allocation / deallocation (same logical warp).
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// D[256 x N] (+)= A[256 x 16] * B[N x 16]^T for the CTA pair, issued by ONE thread of the leader CTA: rows 0..127 of
+// A / D are the leader's (its shared memory / TMEM), rows 128..255 the peer's; each CTA holds N / 2 rows of B.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one arrival on the barrier at the same shared-memory offset in BOTH CTAs of the pair once all prior MMAs retire
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// ---- cluster (CTA pair) plumbing ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+// arrive on a barrier anywhere in the cluster.  Default semantics (.release.cta), as CUTLASS' ClusterBarrier::arrive:
+// what the observer (the leader's MMA thread) consumes are shared-memory operand stages that were published to the
+// async proxy with fence.proxy.async, and TMEM reads closed by tcgen05.fence::before_thread_sync.  An explicit
+// .release.cluster compiles to MEMBAR.ALL.GPU, which also waits for every prefetched global load in flight
+// (measured: proj 87 -> 114 us, res_conv 90 -> 126 us).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // (an .acquire.cluster wait emits CCTL.IVALL per poll)
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA tile load of this CTA's weight rows into ITS shared memory; the bytes are counted on the LEADER's barrier
+// (cta_group::2 form: the mbarrier may live in the peer CTA)
+__device__ __forceinline__ void tma_load_b_2d(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -200,15 +255,16 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
 constexpr uint32_t kALbo = 1024;       // A tile: [8 k-groups][2 MN blocks][8 k rows][128 B]
 constexpr uint32_t kASbo = 2048;
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), A MN-major (bit 15),
-// B K-major, N>>3 in [17,23), M>>4 in [24,29).
+// B K-major, N>>3 in [17,23), M>>4 in [24,29); M = 256: the pair's two 128-row halves (cta_group::2).
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * kTileM) >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------
-// weight packing: W[M][K] fp32 -> per (n_tile, k_block) a contiguous image
-// [hi: tile_n rows x 128 B | lo: tile_n rows x 128 B], rows swizzled exactly as
-// they must sit in shared memory (16 B chunk index XOR row%8).
+// weight packing: W[M][K] fp32 -> per (n_tile, k_block, pair rank) a contiguous image of tile_n rows x 128 B
+// [hi: this rank's tile_n / 2 weight rows | lo: the same rows], rows swizzled exactly as they must sit in
+// shared memory (16 B chunk index XOR row % 8), so a k-block of one CTA is ONE TMA box of [tile_n][128 B].
+// Rank 0 of a pair holds output channels [0, tile_n / 2) of the tile, rank 1 the rest (UMMA cta_group::2 B split).
 // ---------------------------------------------------------------------------
 __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __restrict__ out,
                                        int M, int Mpad, int Kreal, int K, int tile_n) {
@@ -218,10 +274,12 @@ __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __r
     const int kc = (int)(i % (K / 8));        // chunk index along K
     const int m = (int)(i / (K / 8));
     const int kb = kc / 8, c = kc % 8;
-    const int nt = m / tile_n, r = m % tile_n;
+    const int nt = m / tile_n, rt = m % tile_n;
+    const int hn = tile_n / 2;
+    const int rank = rt / hn, r = rt % hn;
     const int KB = K / kBlockK;
-    const size_t half = (size_t)tile_n * 128;
-    uint8_t* img = out + ((size_t)nt * KB + kb) * 2 * half;
+    const size_t half = (size_t)hn * 128;
+    uint8_t* img = out + (((size_t)nt * KB + kb) * 2 + rank) * 2 * half;
     const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((c ^ (r & 7)) << 4);
     __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
@@ -239,14 +297,21 @@ __global__ void pack_weight_mma_kernel(const float* __restrict__ W, uint8_t* __r
 // the GEMM kernel
 // ---------------------------------------------------------------------------
 struct TileCoord { int sample, l0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
+// pair tile -> this CTA's (sample, first position, first output channel).  The last pair of an odd number of
+// position tiles has no tile for rank 1: it gets l0 >= L, which every load / store path already treats as
+// "outside the sample" (zero operand rows, no stores, clipped TMA boxes), so it runs the same barrier protocol.
+__device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile, int rank) {
     TileCoord t;
     const int nt = tile % a.n_tiles;
-    const int rest = tile / a.n_tiles;
-    const int lt = rest % a.l_tiles;
-    t.sample = rest / a.l_tiles;
-    t.l0 = lt * kTileM;
+    const int pos = 2 * (tile / a.n_tiles) + rank;
     t.n0 = nt * a.tile_n;
+    if (pos < a.pos_tiles) {
+        t.sample = pos / a.l_tiles;
+        t.l0 = (pos - t.sample * a.l_tiles) * kTileM;
+    } else {
+        t.sample = 0;
+        t.l0 = a.l_tiles * kTileM;
+    }
     return t;
 }
 
@@ -260,49 +325,52 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile) {
 //   STATS:  accumulate (sum, sumsq) of the output
 template <bool WINDOW, bool ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(SDR_MMA_THREADS(MODE), 1)
-pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // tmap: MODE 3 output, MODE 2 gate
-    // 2 x 32 KB A stages + 2 x 64 KB B stages + 8 KB of tables + 24 KB of epilogue staging + barriers
+pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      // tmap: MODE 3 output, MODE 2 gate
+              const __grid_constant__ CUtensorMap wmap) {                     // wmap: packed weights as [rows][128 B]
+    // 3 x (32 KB A stage + 32 KB B stage) + 8 KB of tables + 24 KB of epilogue staging + barriers
     // (224 KB of the 227 KB an sm_100 CTA can own).  SWIZZLE_128B needs the stage bases 1024 B aligned.
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* a_base = smem;                                                  // kAStages x 32 KB
-    uint8_t* b_base = smem + kAStages * kAStageBytes;                        // kBStages x 64 KB
+    uint8_t* a_base = smem;                                                  // kStages x 32 KB
+    uint8_t* b_base = smem + kStages * kAStageBytes;                         // kStages x 32 KB
     // warp-private tables (no CTA-level barrier in the steady state): per transform warp the
     // (scale, shift) of its 32 channels, double-buffered; per epilogue warp a copy of the tile's bias
-    float2* s_ab = reinterpret_cast<float2*>(b_base + kBStages * kBStageBytes);   // [kProdWarps][2][32]
+    float2* s_ab = reinterpret_cast<float2*>(b_base + kStages * kBStageBytes);    // [kProdWarps][2][32]
     float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 64);    // [kEpiWarps][256]
     float* s_stage = s_bias + kEpiWarps * kMaxTileN;                     // [kStgBufs][16][128], 1024 B aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kStgBufs * kStgFloats);
-    uint64_t* full_bar = bars;                       // [kAStages]  8 transform warps + the TMA thread (+tx bytes)
-    uint64_t* empty_bar = full_bar + kAStages;       // [kAStages]  one tcgen05.commit
-    uint64_t* tfull_bar = empty_bar + kAStages;      // [2]
+    // Barriers exist at the same offsets in both CTAs of the pair.
+    //   full_bar   (the LEADER's copy is used): 8 + 8 transform warps of both CTAs + the leader's TMA thread, and the
+    //              tx bytes of both CTAs' weight loads; waited on by the leader's MMA thread.
+    //   empty_bar  (each CTA's own copy): one multicast tcgen05.commit per use, waited on by the CTA's producers.
+    //   tfull_bar  (each CTA's own copy): multicast commit at the end of a tile, waited on by the CTA's epilogue.
+    //   tempty_bar (the LEADER's copy): 4 + 4 epilogue warps of both CTAs; waited on by the leader's MMA thread.
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = full_bar + kStages;        // [kStages]
+    uint64_t* tfull_bar = empty_bar + kStages;       // [2]
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-    uint64_t* gfull_bar = tempty_bar + 2;            // [kStgBufs]  gate tile landed (TMA tx bytes)
-    uint64_t* gempty_bar = gfull_bar + kStgBufs;     // [kStgBufs]  all 128 epilogue threads have read it
+    uint64_t* gfull_bar = tempty_bar + 2;            // [kStgBufs]  gate tile landed (TMA tx bytes); CTA-local
+    uint64_t* gempty_bar = gfull_bar + kStgBufs;     // [kStgBufs]  all 128 epilogue threads have read it; CTA-local
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gempty_bar + kStgBufs);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-#if SDR_MMA_EPI_WARPS != 4
-    constexpr int EW = mma_epi_warps(MODE), EG = EW / 4;
-    constexpr int kMmaWarp = EW, kTmaWarp = EW + 1, kProdWarp0 = EW + 2;
-#endif
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int KB = a.K / kBlockK;
-    const uint32_t bhalf = (uint32_t)a.tile_n * 128;
+    const int rank = (int)cluster_ctarank();         // 0 = leader (issues the pair's MMAs)
+    const int tile0 = (int)cluster_id_x();           // pair tiles of this pair: tile0, tile0 + tstep, ...
+    const int tstep = (int)num_clusters_x();
+    const uint32_t bhalf = (uint32_t)(a.tile_n / 2) * 128;     // bytes of this CTA's rows in one bf16 weight image
 
     if (warp == kTmaWarp && lane == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&full_bar[s], kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
-#if SDR_MMA_EPI_WARPS == 4
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
-#else
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW * 32); }
-#endif
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2 * kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * kEpiWarps); }
         for (int s = 0; s < kStgBufs; ++s) { mbar_init(&gfull_bar[s], 1); mbar_init(&gempty_bar[s], kEpiWarps * 32); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                              // the peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -330,8 +398,8 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
         auto advance = [&](Cur& c) {              // next (tile, k-block) of this CTA; tile >= num_tiles == end
             if (++c.kb == KB) {
                 c.kb = 0;
-                c.tile += gridDim.x;
-                if (c.tile < a.num_tiles) c.tc = decode_tile(a, c.tile);
+                c.tile += tstep;
+                if (c.tile < a.num_tiles) c.tc = decode_tile(a, c.tile, rank);
             }
         };
         // one channel row (4 positions) of step c
@@ -376,6 +444,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             }
         };
 
+        // this CTA's transform warps signal the LEADER's full barrier (the leader's MMA thread consumes both CTAs' stages)
+        const uint32_t full_leader0 = map_to_rank(smem_u32(&full_bar[0]), 0);      // consecutive 8-byte barriers
+        static_assert(kStages == 3, "stage -> barrier address below");
 #if SDR_MMA_LEAN_PRODUCER
         // The ncu source view of the loop below (profiles/r01d_tma_epilogue.md): 400 instructions per k-block and warp, of
         // which only ~200 are the transform; the rest re-derives three (tile, k-block) cursors, 64-bit row addresses and
@@ -394,9 +465,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                 const int l = t.l0 + (lane >> 3) * 32;
                 return l < a.L ? a.x + (((size_t)t.sample * a.K + (size_t)kb * kBlockK + pw * 8 + (lane & 7)) * Ls + l) : nullptr;
             };
-            int tile = blockIdx.x, kb = 0;
+            int tile = tile0, kb = 0;
             if (tile < a.num_tiles) {
-                TileCoord tc = decode_tile(a, tile);
+                TileCoord tc = decode_tile(a, tile, rank);
                 const float* cp0 = row0(tc, 0);
                 float4 v[8];
 #pragma unroll
@@ -409,8 +480,8 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                 auto pf_advance = [&]() {
                     if (++pkb == KB) {
                         pkb = 0;
-                        ptile += gridDim.x;
-                        pp = ptile < a.num_tiles ? pf0(decode_tile(a, ptile), 0) : nullptr;
+                        ptile += tstep;
+                        pp = ptile < a.num_tiles ? pf0(decode_tile(a, ptile, rank), 0) : nullptr;
                     } else if (pp) {
                         pp += kstep;
                     }
@@ -418,6 +489,8 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                 pf_advance();
                 if (ptile < a.num_tiles && pp) prefetch_l2(pp);
                 uint32_t it = 0;
+                int stage = 0;
+                uint32_t phase = 0;
                 float mean = 0.f, rstd = 1.f;          // of the current tile's sample
 #pragma unroll 1
                 while (tile < a.num_tiles) {
@@ -426,14 +499,12 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                     const float* np = cp0 ? cp0 + kstep : nullptr;
                     if (n.kb == KB) {
                         n.kb = 0;
-                        n.tile = tile + gridDim.x;
+                        n.tile = tile + tstep;
                         np = nullptr;
-                        if (n.tile < a.num_tiles) { n.tc = decode_tile(a, n.tile); np = row0(n.tc, 0); }
+                        if (n.tile < a.num_tiles) { n.tc = decode_tile(a, n.tile, rank); np = row0(n.tc, 0); }
                     }
                     pf_advance();
                     if (ptile < a.num_tiles && pp) prefetch_l2(pp);
-                    const int stage = it % kAStages;
-                    const uint32_t phase = (it / kAStages) & 1;
                     {                                  // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
                         float aa = 1.f, bb = 0.f;
                         if (has_norm) {
@@ -484,8 +555,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                     }
                     fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    if (lane == 0) mbar_arrive_cluster(full_leader0 + 8u * (uint32_t)stage);
                     ++it;
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                     tile = n.tile; kb = n.kb; tc = n.tc; cp0 = np;
                 }
             }
@@ -493,9 +565,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
 #endif
         {
         Cur c;
-        c.tile = blockIdx.x; c.kb = 0;
+        c.tile = tile0; c.kb = 0;
         if (c.tile < a.num_tiles) {
-            c.tc = decode_tile(a, c.tile);
+            c.tc = decode_tile(a, c.tile, rank);
             float4 v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = load_row(c, e);
@@ -503,14 +575,14 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             Cur cp = c;
             advance(cp); prefetch_step(cp);
             uint32_t it = 0;
+            int stage = 0;
+            uint32_t phase = 0;                    // parity of the ring pass (it / kStages)
             float mean = 0.f, rstd = 1.f;          // of the current tile's sample
 #pragma unroll 1
             while (c.tile < a.num_tiles) {
                 Cur n = c;
                 advance(n);                        // next step (n.tile >= num_tiles: none)
                 advance(cp); prefetch_step(cp);    // two steps ahead
-                const int stage = it % kAStages;
-                const uint32_t phase = (it / kAStages) & 1;
                 {                                  // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
                     float aa = 1.f, bb = 0.f;
                     if (has_norm) {
@@ -560,47 +632,53 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                 }
                 fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (lane == 0) mbar_arrive_cluster(full_leader0 + 8u * (uint32_t)stage);
                 ++it;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
                 c = n;
             }
         }
         }
     } else if (warp == kTmaWarp) {
-        // ===================== B-operand (weights) bulk-TMA producer =====================
+        // ===================== B-operand (weights) TMA producer =====================
+        // Each CTA loads its own tile_n / 2 weight rows (hi | lo = one [tile_n][128 B] box of the packed image) into
+        // its own stage; the bytes of BOTH CTAs are expected by, and counted on, the leader's full barrier.
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const uint32_t full_leader0 = map_to_rank(smem_u32(&full_bar[0]), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = tile0; tile < a.num_tiles; tile += tstep) {
                 const int nt = tile % a.n_tiles;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int stage = it % kBStages;
-                    const uint32_t phase = (it / kBStages) & 1;
+                for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], 2 * bhalf);
-                    const uint8_t* src = a.wpk + ((size_t)nt * KB + kb) * 2 * bhalf;
-                    bulk_g2s(b_base + (size_t)stage * kBStageBytes, src, 2 * bhalf, &full_bar[stage]);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 4 * bhalf);   // 2 CTAs x (hi + lo)
+                    const int row = ((nt * KB + kb) * 2 + rank) * a.tile_n;              // first row of this CTA's box
+                    tma_load_b_2d(b_base + (size_t)stage * kBStageBytes, &wmap,
+                                  full_leader0 + 8u * (uint32_t)stage, 0, row);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (one thread of the leader CTA) =====================
+        if (lane == 0 && rank == 0) {
             const uint32_t idesc = umma_idesc_bf16(a.tile_n);
-            uint32_t it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
+            uint32_t ti = 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++ti) {
                 const int acc = ti & 1;
                 const uint32_t aphase = (ti >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], aphase ^ 1);
+                mbar_wait_cluster(&tempty_bar[acc], aphase ^ 1);          // both CTAs' epilogues drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxTileN;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int sa = it % kAStages, sb = sa;
-                    mbar_wait(&full_bar[sa], (it / kAStages) & 1);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait_cluster(&full_bar[stage], phase);           // A of both CTAs transformed, B of both landed
                     tc_fence_after();
-                    const uint32_t sa_hi = smem_u32(a_base + (size_t)sa * kAStageBytes);
+                    const uint32_t sa_hi = smem_u32(a_base + (size_t)stage * kAStageBytes);
                     const uint32_t sa_lo = sa_hi + kAHalf;
-                    const uint32_t sb_hi = smem_u32(b_base + (size_t)sb * kBStageBytes);
+                    const uint32_t sb_hi = smem_u32(b_base + (size_t)stage * kBStageBytes);
                     const uint32_t sb_lo = sb_hi + bhalf;
 #pragma unroll
                     for (int ks = 0; ks < kBlockK / 16; ++ks) {
@@ -613,25 +691,18 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                         umma_bf16(d_tmem, dal, dbh, idesc, 1u);
                         umma_bf16(d_tmem, dah, dbl, idesc, 1u);
                     }
-                    umma_commit(&empty_bar[sa]);              // both slots free once these MMAs retire
+                    umma_commit(&empty_bar[stage]);           // frees this stage in BOTH CTAs once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                 // accumulator ready for the epilogue
+                umma_commit(&tfull_bar[acc]);                 // accumulator ready for both CTAs' epilogues
             }
         }
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
-#if SDR_MMA_EPI_WARPS == 4
         const int q = warp;                 // TMEM lane quarter of this warp
         const size_t Ls = (size_t)a.L;
         const int nchunks = a.tile_n / kEpiChunk;
-#else
-        const int q = warp & 3;             // TMEM lane quarter of this warp
-        // with two warps per quarter (EG == 2) warp w owns the columns [col0, col0 + tile_n / 2) of the tile
-        const int col0 = (warp >> 2) * (a.tile_n / EG);
-        const size_t Ls = (size_t)a.L;
-        const int nchunks = a.tile_n / kEpiChunk / EG;
-#endif
         // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
         constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
         constexpr bool kGateTma = SDR_MMA_BULK && MODE == 2;    // gate tiles arrive through TMA loads into the staging ring
@@ -649,25 +720,26 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             if (++gcur.b == kStgBufs) { gcur.b = 0; ++gcur.k; }
             if (++gcur.c == gcur.nch) {
                 gcur.c = 0;
-                gcur.tile += gridDim.x;
-                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile); gcur.nch = gate_nch(gcur.tc); }
+                gcur.tile += tstep;
+                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile, rank); gcur.nch = gate_nch(gcur.tc); }
             }
         };
         if constexpr (kGateTma) {
             if (tid == 0) {
-                gcur.tile = blockIdx.x;
-                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile); gcur.nch = gate_nch(gcur.tc); }
+                gcur.tile = tile0;
+                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile, rank); gcur.nch = gate_nch(gcur.tc); }
                 gate_issue();
                 gate_issue();
             }
         }
+        const uint32_t tempty_leader0 = map_to_rank(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_leader1 = map_to_rank(smem_u32(&tempty_bar[1]), 0);
         uint32_t ti = 0;
 #pragma unroll 1
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++ti) {
+        for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++ti) {
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
-            const TileCoord tc = decode_tile(a, tile);
-#if SDR_MMA_EPI_WARPS == 4
+            const TileCoord tc = decode_tile(a, tile, rank);
             float* const sb = s_bias + q * kMaxTileN;          // this warp's private copy of the tile's bias
             const int ncols = min(a.tile_n, a.M - tc.n0);      // real output channels in this tile (< tile_n: padding)
             __syncwarp();                                      // the warp is done with the previous tile's bias
@@ -677,26 +749,11 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
             const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0) * Ls + l;       // (m = n0, l)
-#else
-            float* const sb = s_bias + warp * (kMaxTileN / EG);    // this warp's private copy of its columns' bias
-            const int ncols = min(a.tile_n, a.M - tc.n0) - col0;   // real output channels among this warp's columns
-            __syncwarp();                                      // the warp is done with the previous tile's bias
-            for (int j = lane; j < a.tile_n / EG; j += 32)
-                sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + col0 + j) : 0.f;
-            __syncwarp();
-            const int l = tc.l0 + q * 32 + lane;
-            const bool valid = l < a.L;
-            const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0 + col0) * Ls + l;   // (m = n0 + col0, l)
-#endif
             // MODE 1: residual (may alias y: in-place skip connection); MODE 2: gate operand of this tile
             const float* ep = nullptr;
             if (MODE == 1) ep = a.residual + out_row0;
             if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
-#if SDR_MMA_EPI_WARPS == 4
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
-#else
-            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN + col0);
-#endif
             float st_s = 0.f, st_q = 0.f;
             if (MODE == 1 || (MODE == 2 && !kGateTma)) {  // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
@@ -861,7 +918,8 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            __syncwarp();                                  // every lane's tcgen05.ld of this accumulator has completed
+            if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
             if (STATS) {
                 st_s = warp_sum(st_s);
                 st_q = warp_sum(st_q);
@@ -876,6 +934,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap) {   // 
     if (tid == 0) bulk_wait_all();              // staged output tiles have left shared memory and are written
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                         // the peer no longer signals this CTA's barriers or reads its operand stages
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -908,10 +967,10 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
-constexpr size_t kMmaSmemBytes = (size_t)kAStages * kAStageBytes + (size_t)kBStages * kBStageBytes +
+constexpr size_t kMmaSmemBytes = (size_t)kStages * (kAStageBytes + kBStageBytes) +
                                  kProdWarps * 64 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
                                  (size_t)kStgBufs * kStgFloats * sizeof(float) +
-                                 (2 * kAStages + 4 + 2 * kStgBufs + 2) * sizeof(uint64_t);
+                                 (2 * kStages + 4 + 2 * kStgBufs + 2) * sizeof(uint64_t);
 static_assert(kEpiChunk == 16, "tmem_ld16 is hard-wired in the epilogue");
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
@@ -947,6 +1006,70 @@ static int make_tile_map(CUtensorMap* tm, const float* y, int samples, int M, in
     return r == CUDA_SUCCESS ? SDR_OK : SDR_ERR_UNSUPPORTED;
 }
 
+// Tensor map of a packed weight buffer seen as [rows][128 B]: one box = the tile_n rows (hi | lo) of one
+// (n_tile, k_block, pair rank) image, already in shared-memory order (no TMA swizzle).
+static int make_weight_map(CUtensorMap* tm, const void* wpk, size_t bytes, int tile_n) {
+    memset(tm, 0, sizeof(*tm));
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return SDR_ERR_CUDA;
+    const cuuint64_t dims[2] = {32, (cuuint64_t)(bytes / 128)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)tile_n};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(wpk), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SDR_OK : SDR_ERR_UNSUPPORTED;
+}
+
+// Persistent launch as clusters of two CTAs (a CTA pair shares one TPC): as many pairs as can be resident at once
+// (queried once per kernel instantiation and device), never more than there are pair tiles.
+// (All instantiations share one function-pointer type, so the per-kernel state is keyed by the pointer, not by Kern.)
+struct PairLaunchInfo { const void* fn; int dev; int max_pairs; };
+static std::mutex g_pair_mutex;
+static std::vector<PairLaunchInfo> g_pair_info;
+
+template <typename Kern>
+static int launch_pairs(Kern kern, const MmaArgs& a, const CUtensorMap& tmap, const CUtensorMap& wmap, cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SDR_ERR_CUDA;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kMmaThreads, 1, 1);
+    cfg.dynamicSmemBytes = kMmaSmemBytes;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_pairs = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pair_mutex);
+        for (const PairLaunchInfo& e : g_pair_info)
+            if (e.fn == reinterpret_cast<const void*>(kern) && e.dev == dev) { max_pairs = e.max_pairs; break; }
+        if (max_pairs == 0) {                     // first launch of this kernel on this device
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess) {
+                cudaGetLastError();
+                return SDR_ERR_CUDA;
+            }
+            int sms = 0, n = 0;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
+            cfg.gridDim = dim3((unsigned)(sms & ~1), 1, 1);
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2; }
+            max_pairs = n < sms / 2 ? n : sms / 2;
+            if (max_pairs < 1) max_pairs = 1;
+            g_pair_info.push_back(PairLaunchInfo{reinterpret_cast<const void*>(kern), dev, max_pairs});
+            if (getenv("SDR_B200_DEBUG")) fprintf(stderr, "[sdr] pair kernel %p: %d SMs, %d resident pairs (occupancy query %d)\n",
+                                                  reinterpret_cast<const void*>(kern), sms, max_pairs, n);
+        }
+    }
+    const int pairs = a.num_tiles < max_pairs ? a.num_tiles : max_pairs;
+    cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+    if (cudaLaunchKernelEx(&cfg, kern, a, tmap, wmap) != cudaSuccess) { cudaGetLastError(); return SDR_ERR_CUDA; }
+    return SDR_OK;
+}
+
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
                          const float* residual, const float* gate, int gate_channels,
                          float* y, double* stats_out, int samples, int M, int K, int L,
@@ -965,13 +1088,11 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     a.tile_n = mma_tile_n(M);
     a.n_tiles = mma_pad_m(M) / a.tile_n;
     a.l_tiles = (L + kTileM - 1) / kTileM;
-    const long long tiles = (long long)samples * a.l_tiles * a.n_tiles;
-    if (tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    const long long pos_tiles = (long long)samples * a.l_tiles;
+    const long long tiles = (pos_tiles + 1) / 2 * a.n_tiles;
+    if (pos_tiles > 0x3fffffffLL || tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    a.pos_tiles = (int)pos_tiles;
     a.num_tiles = (int)tiles;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
-    const int grid = (int)(tiles < sms ? tiles : sms);
     const bool act = nin.prelu != nullptr;
     // in-place skip connection (every U-ConvBlock's res_conv): the residual add happens in L2 (bulk reduce-add)
     const bool inplace = SDR_MMA_BULK && residual == y && (reinterpret_cast<uintptr_t>(y) % 16) == 0;
@@ -981,13 +1102,10 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     CUtensorMap ymap;      // MODE 3: the in-place output; MODE 2: the gate tensor [samples][gate_channels][L]
     if (int rc = mode == 2 ? make_tile_map(&ymap, gate, samples, gate_channels, L, SDR_MMA_BULK)
                            : make_tile_map(&ymap, y, samples, M, L, mode == 3)) return rc;
+    CUtensorMap wmap;
+    if (int rc = make_weight_map(&wmap, wpk, pointwise_mma_packed_bytes(M, K), a.tile_n)) return rc;
 #define SDR_MMA_CASE(A, MD, ST)                                                                                   \
-    if (act == A && mode == MD && stats == ST) {                                                                  \
-        if (cudaFuncSetAttribute(pw_mma_kernel<false, A, MD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                 (int)kMmaSmemBytes) != cudaSuccess) return SDR_ERR_CUDA;                         \
-        pw_mma_kernel<false, A, MD, ST><<<grid, SDR_MMA_THREADS(MD), kMmaSmemBytes, st>>>(a, ymap);                             \
-        return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;                                         \
-    }
+    if (act == A && mode == MD && stats == ST) return launch_pairs(pw_mma_kernel<false, A, MD, ST>, a, ymap, wmap, st);
     SDR_MMA_CASE(false, 0, false) SDR_MMA_CASE(false, 0, true)
     SDR_MMA_CASE(true, 0, false)  SDR_MMA_CASE(true, 0, true)
     SDR_MMA_CASE(false, 1, false) SDR_MMA_CASE(false, 1, true)
@@ -1030,25 +1148,16 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     a.tile_n = mma_tile_n(N);
     a.n_tiles = mma_pad_m(N) / a.tile_n;
     a.l_tiles = (L + kTileM - 1) / kTileM;
-    const long long tiles = (long long)B * a.l_tiles * a.n_tiles;
-    if (tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    const long long pos_tiles = (long long)B * a.l_tiles;
+    const long long tiles = (pos_tiles + 1) / 2 * a.n_tiles;
+    if (pos_tiles > 0x3fffffffLL || tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    a.pos_tiles = (int)pos_tiles;
     a.num_tiles = (int)tiles;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDR_ERR_CUDA;
-    const int grid = (int)(tiles < sms ? tiles : sms);
-    CUtensorMap ymap;
+    CUtensorMap ymap, wmap;
     if (int rc = make_tile_map(&ymap, enc, B, N, L, false)) return rc;
-    if (stats) {
-        if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
-            return SDR_ERR_CUDA;
-        pw_mma_kernel<true, false, 0, true><<<grid, SDR_MMA_THREADS(0), kMmaSmemBytes, st>>>(a, ymap);
-    } else {
-        if (cudaFuncSetAttribute(pw_mma_kernel<true, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes) != cudaSuccess)
-            return SDR_ERR_CUDA;
-        pw_mma_kernel<true, false, 0, false><<<grid, SDR_MMA_THREADS(0), kMmaSmemBytes, st>>>(a, ymap);
-    }
-    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+    if (int rc = make_weight_map(&wmap, wpk, encoder_mma_packed_bytes(N, A, Kk), a.tile_n)) return rc;
+    if (stats) return launch_pairs(pw_mma_kernel<true, false, 0, true>, a, ymap, wmap, st);
+    return launch_pairs(pw_mma_kernel<true, false, 0, false>, a, ymap, wmap, st);
 }
 
 }  // namespace sdr
