@@ -41,19 +41,43 @@ namespace sdr {
 // for a third pipeline stage.
 constexpr int kTileM = 128;            // positions per CTA tile (UMMA M per CTA, TMEM lanes)
 constexpr int kBlockK = 64;            // channels per k-block = one 128 B swizzle row of bf16
-constexpr int kStages = 3;             // A (activation) and B (weight) stages share one full/empty barrier ring
+#ifndef SDR_MMA_RAW_TMA
+#define SDR_MMA_RAW_TMA 1              // 1: raw activation tiles arrive by TMA into a shared-memory ring, the transform warps
+#endif                                 //    work shared -> shared (no global loads, cursors or prefetch registers in their loop)
+#if SDR_MMA_RAW_TMA
+constexpr int kStages = 2;             // A (transformed activations) and B (weights) stages share one full/empty barrier ring
+constexpr int kRawStages = 2;          // fp32 [64 channels][128 positions] tiles landed by TMA, read once by the transform warps
+#else
+constexpr int kStages = 3;
+constexpr int kRawStages = 0;
+#endif
+constexpr int kRawStageBytes = kTileM * 64 * 4;              // 32 KB
 constexpr int kMaxTileN = 256;         // output channels per tile (UMMA N, TMEM columns per accumulator stage)
 constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
 constexpr int kBHalfMax = (kMaxTileN / 2) * 128;             // 16 KB: this CTA's tile_n / 2 weight rows, one bf16 image
 constexpr int kAStageBytes = 2 * kAHalf;                     // 32 KB: hi + lo
 constexpr int kBStageBytes = 2 * kBHalfMax;                  // 32 KB: hi + lo
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5, kProdWarp0 = 6, kProdWarps = 8;
-constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps);   // 448
+// Warp roles: [0, 8) epilogue slots (the plain-store exit, MODE 0, uses all 8: two warps per TMEM lane quarter, each
+// owning half of the tile's columns; the staged exits, MODE 2 / 3, and MODE 1 use the first 4), 8 MMA issuer,
+// 9 weight TMA, [10, 18) operand transform, 18 raw activation TMA.  The role timeline (tools/trace_gemm.py) showed
+// proj bound by its 4 epilogue warps: 4.1 us to drain a tile + 0.8 us between tiles against 4.0 us of MMA time.
+constexpr int kEpiSlots = 8, kEpiWarps = 4, kMmaWarp = 8, kTmaWarp = 9, kProdWarp0 = 10, kProdWarps = 8;
+constexpr int epi_warps(int mode) { return mode == 0 ? 8 : 4; }
+constexpr int kRawWarp = kProdWarp0 + kProdWarps;             // 18: raw activation tile TMA producer (SDR_MMA_RAW_TMA)
+constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps + (SDR_MMA_RAW_TMA ? 1 : 0));   // 608 (576 without the raw loader)
 #define SDR_MMA_THREADS(MODE) kMmaThreads
 constexpr int kProdThreads = 32 * kProdWarps;                 // 256
 #ifndef SDR_MMA_LEAN_PRODUCER
 #define SDR_MMA_LEAN_PRODUCER 1         // transform loop with pointer-bumped cursors and the (scale, shift) table read before the
 #endif                                  // stage wait (round-2 A/B on the B200: res_conv 90 -> 82 us, bottleneck 84 -> 78 us)
+#ifndef SDR_MMA_TRACE
+#define SDR_MMA_TRACE 0                 // diagnostic build (tools/trace_gemm.py): per-role clock64 timeline of CTA 0
+#endif
+#if SDR_MMA_TRACE
+#define SDR_TR(role, idx, slot) do { if (blockIdx.x == 0 && a.trace && (idx) < 256) a.trace[((role) * 256 + (idx)) * 4 + (slot)] = clock64(); } while (0)
+#else
+#define SDR_TR(role, idx, slot) do { } while (0)
+#endif
 #ifndef SDR_MMA_BULK
 #define SDR_MMA_BULK 1                  // 1: the in-place skip connection (mode 3) leaves through staging tiles + TMA reduce-add
 #endif
@@ -80,6 +104,9 @@ struct MmaArgs {
     int epilogue;
     // window mode (encoder Conv1d as a GEMM without im2col): operand element (position p, k = a*win_k + j)
     // is wav[sample, a, win_hop * p + j - win_pad] (zero outside [0, win_T)); x = wav, K = padded taps
+#if SDR_MMA_TRACE
+    long long* trace;     // diagnostic build: [role 0..5][256][4] clock64 stamps of pair 0's leader CTA
+#endif
     int win_k;            // 0 = normal pointwise mode
     int win_hop, win_pad, win_a;
     long long win_T;
@@ -326,7 +353,8 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile, int
 template <bool WINDOW, bool ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(SDR_MMA_THREADS(MODE), 1)
 pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      // tmap: MODE 3 output, MODE 2 gate
-              const __grid_constant__ CUtensorMap wmap) {                     // wmap: packed weights as [rows][128 B]
+              const __grid_constant__ CUtensorMap wmap,                       // wmap: packed weights as [rows][128 B]
+              const __grid_constant__ CUtensorMap xmap) {                     // xmap: activations [samples][K][L], box [64][128]
     // 3 x (32 KB A stage + 32 KB B stage) + 8 KB of tables + 24 KB of epilogue staging + barriers
     // (224 KB of the 227 KB an sm_100 CTA can own).  SWIZZLE_128B needs the stage bases 1024 B aligned.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -334,8 +362,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
     uint8_t* b_base = smem + kStages * kAStageBytes;                         // kStages x 32 KB
     // warp-private tables (no CTA-level barrier in the steady state): per transform warp the
     // (scale, shift) of its 32 channels, double-buffered; per epilogue warp a copy of the tile's bias
-    float2* s_ab = reinterpret_cast<float2*>(b_base + kStages * kBStageBytes);    // [kProdWarps][2][32]
-    float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 64);    // [kEpiWarps][256]
+    uint8_t* r_base = b_base + kStages * kBStageBytes;                       // kRawStages x 32 KB
+    float2* s_ab = reinterpret_cast<float2*>(r_base + kRawStages * kRawStageBytes);   // [kProdWarps][2][32]
+    float* s_bias = reinterpret_cast<float*>(s_ab + kProdWarps * 64);    // [4][256] or [8][128]: per-warp bias copies
     float* s_stage = s_bias + kEpiWarps * kMaxTileN;                     // [kStgBufs][16][128], 1024 B aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kStgBufs * kStgFloats);
     // Barriers exist at the same offsets in both CTAs of the pair.
@@ -343,14 +372,16 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
     //              tx bytes of both CTAs' weight loads; waited on by the leader's MMA thread.
     //   empty_bar  (each CTA's own copy): one multicast tcgen05.commit per use, waited on by the CTA's producers.
     //   tfull_bar  (each CTA's own copy): multicast commit at the end of a tile, waited on by the CTA's epilogue.
-    //   tempty_bar (the LEADER's copy): 4 + 4 epilogue warps of both CTAs; waited on by the leader's MMA thread.
+    //   tempty_bar (the LEADER's copy): the epilogue warps of both CTAs (2 x 8 or 2 x 4); waited on by the leader's MMA thread.
     uint64_t* full_bar = bars;                       // [kStages]
     uint64_t* empty_bar = full_bar + kStages;        // [kStages]
     uint64_t* tfull_bar = empty_bar + kStages;       // [2]
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
     uint64_t* gfull_bar = tempty_bar + 2;            // [kStgBufs]  gate tile landed (TMA tx bytes); CTA-local
     uint64_t* gempty_bar = gfull_bar + kStgBufs;     // [kStgBufs]  all 128 epilogue threads have read it; CTA-local
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gempty_bar + kStgBufs);
+    uint64_t* rfull_bar = gempty_bar + kStgBufs;     // [kRawStages] raw tile landed (TMA tx bytes); CTA-local
+    uint64_t* rempty_bar = rfull_bar + 2;            // [kRawStages] all 8 transform warps hold it in registers; CTA-local
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(rempty_bar + 2);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
     const int tid = threadIdx.x;
@@ -363,8 +394,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
 
     if (warp == kTmaWarp && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2 * kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * epi_warps(MODE)); }
         for (int s = 0; s < kStgBufs; ++s) { mbar_init(&gfull_bar[s], 1); mbar_init(&gempty_bar[s], kEpiWarps * 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&rfull_bar[s], 1); mbar_init(&rempty_bar[s], kProdWarps); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(s_tmem, 512);
@@ -374,7 +406,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp >= kProdWarp0) {
+    if (warp >= kProdWarp0 && warp < kProdWarp0 + kProdWarps) {
         // ===================== A-operand transform producers =====================
         // Warp w owns the 8 channels of k-group w of every k-block; lane i owns positions 4i..4i+3.
         // Per channel a thread does ONE float4 load (a warp reads a 512 B row segment), the folded
@@ -446,8 +478,100 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
 
         // this CTA's transform warps signal the LEADER's full barrier (the leader's MMA thread consumes both CTAs' stages)
         const uint32_t full_leader0 = map_to_rank(smem_u32(&full_bar[0]), 0);      // consecutive 8-byte barriers
-        static_assert(kStages == 3, "stage -> barrier address below");
-#if SDR_MMA_LEAN_PRODUCER
+#if SDR_MMA_RAW_TMA
+        // Shared -> shared transform.  The raw fp32 tile [64 channels][128 positions] of this k-block was landed by the
+        // raw loader warp's TMA (zero-filled outside the sample), so this loop has no global loads, no L2 prefetch and no
+        // address cursors: 8 conflict-free LDS.128 (a warp reads one 512 B channel row), release of the raw slot, the
+        // folded normalisation (+PReLU), the bf16 hi/lo split and the swizzled stores.  The ncu source view of the
+        // register-prefetch loop had 40 % of its samples on the scoreboard of the prefetched loads and 20 % in cursor code.
+        if constexpr (!WINDOW) {
+            int tile = tile0, kb = 0;
+            if (tile < a.num_tiles) {
+                TileCoord tc = decode_tile(a, tile, rank);
+                Cur c0; c0.tile = tile; c0.kb = 0; c0.tc = tc;
+                Aux aux = load_aux(c0);
+                uint32_t it = 0;
+                int stage = 0, rs = 0;
+                uint32_t phase = 0, rphase = 0;
+                float mean = 0.f, rstd = 1.f;          // of the current tile's sample
+                const uint32_t raw_lane = (uint32_t)(pw * 8) * 512u + (uint32_t)lane * 16u;
+#pragma unroll 1
+                while (tile < a.num_tiles) {
+                    Cur n; n.tile = tile; n.kb = kb + 1; n.tc = tc;
+                    if (n.kb == KB) {
+                        n.kb = 0;
+                        n.tile = tile + tstep;
+                        if (n.tile < a.num_tiles) n.tc = decode_tile(a, n.tile, rank);
+                    }
+                    {                                  // y = x * aa + bb  ==  gamma * (x - mean) * rstd + beta
+                        float aa = 1.f, bb = 0.f;
+                        if (has_norm) {
+                            if (kb == 0) {
+                                const double mu = aux.s0 * inv_count;
+                                double var = aux.s1 * inv_count - mu * mu;
+                                var = var < 0.0 ? 0.0 : var;
+                                mean = (float)mu;
+                                rstd = rsqrtf((float)var + kGlnEps);
+                            }
+                            aa = aux.g * rstd;
+                            bb = aux.b - mean * aa;
+                        }
+                        if (lane < 8) my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
+                        aux = load_aux(n);
+                    }
+                    __syncwarp();                      // table visible to the warp (reuse is ordered by the next __syncwarp)
+                    const float2* tab = my_tab + (it & 1) * 8;
+                    float2 abv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) abv[e] = tab[e];
+                    if (pw == 0 && lane == 0) SDR_TR(0, it, 0);
+                    mbar_wait(&rfull_bar[rs], rphase);                          // raw tile landed
+                    if (pw == 0 && lane == 0) SDR_TR(0, it, 1);
+                    const uint8_t* rp = r_base + (size_t)rs * kRawStageBytes + raw_lane;
+                    float4 v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(rp + e * 512);
+                    __syncwarp();                      // every lane holds its quads: the slot may be refilled
+                    if (lane == 0) mbar_arrive(&rempty_bar[rs]);
+                    if (++rs == kRawStages) { rs = 0; rphase ^= 1; }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (pw == 0 && lane == 0) SDR_TR(0, it, 2);
+                    uint8_t* a_hi = a_base + (size_t)stage * kAStageBytes;
+                    uint8_t* a_lo = a_hi + kAHalf;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 ab = abv[e];
+                        float y[4] = {fmaf(v[e].x, ab.x, ab.y), fmaf(v[e].y, ab.x, ab.y),
+                                      fmaf(v[e].z, ab.x, ab.y), fmaf(v[e].w, ab.x, ab.y)};
+                        if (ACT) {                     // PReLU in 2 ops: max(y, s*y) for s <= 1, min otherwise
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float t = y[u] * slope;
+                                y[u] = slope_le1 ? fmaxf(y[u], t) : fminf(y[u], t);
+                            }
+                        }
+                        uint32_t hb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) hb[u] = __float_as_uint(y[u]) & 0xffff0000u;
+                        const uint32_t h01 = __byte_perm(hb[0], hb[1], 0x7632), h23 = __byte_perm(hb[2], hb[3], 0x7632);
+                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[0] - __uint_as_float(hb[0]), y[1] - __uint_as_float(hb[1]));
+                        const __nv_bfloat162 l23 = __floats2bfloat162_rn(y[2] - __uint_as_float(hb[2]), y[3] - __uint_as_float(hb[3]));
+                        const uint32_t off = lane_off + (uint32_t)e * 128 + ((lane_chunk ^ (uint32_t)e) << 4);
+                        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
+                        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01),
+                                                                            *reinterpret_cast<const uint32_t*>(&l23));
+                    }
+                    fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(full_leader0 + 8u * (uint32_t)stage);
+                    if (pw == 0 && lane == 0) SDR_TR(0, it, 3);
+                    ++it;
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    tile = n.tile; kb = n.kb; tc = n.tc;
+                }
+            }
+        } else
+#elif SDR_MMA_LEAN_PRODUCER
         // The ncu source view of the loop below (profiles/r01d_tma_epilogue.md): 400 instructions per k-block and warp, of
         // which only ~200 are the transform; the rest re-derives three (tile, k-block) cursors, 64-bit row addresses and
         // bounds tests per row, and a quarter of the stall samples sit on the table LDS feeding each channel's first FFMA.
@@ -639,18 +763,42 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
             }
         }
         }
+    } else if (SDR_MMA_RAW_TMA && warp == kRawWarp) {
+        // ===================== raw activation tiles: TMA producer (CTA-local ring) =====================
+        if (lane == 0 && !WINDOW) {
+            int rs = 0;
+            uint32_t rphase = 0;
+            [[maybe_unused]] int trit = 0;
+            for (int tile = tile0; tile < a.num_tiles; tile += tstep) {
+                const TileCoord tc = decode_tile(a, tile, rank);
+                for (int kb = 0; kb < KB; ++kb) {
+                    SDR_TR(1, trit, 0);
+                    mbar_wait(&rempty_bar[rs], rphase ^ 1);
+                    SDR_TR(1, trit, 1);
+                    ++trit;
+                    mbar_arrive_expect_tx(&rfull_bar[rs], kRawStageBytes);
+                    tma_load_3d(r_base + (size_t)rs * kRawStageBytes, &xmap, &rfull_bar[rs], tc.l0, kb * kBlockK, tc.sample);
+                    if (++rs == kRawStages) { rs = 0; rphase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
     } else if (warp == kTmaWarp) {
         // ===================== B-operand (weights) TMA producer =====================
         // Each CTA loads its own tile_n / 2 weight rows (hi | lo = one [tile_n][128 B] box of the packed image) into
         // its own stage; the bytes of BOTH CTAs are expected by, and counted on, the leader's full barrier.
         if (lane == 0) {
             const uint32_t full_leader0 = map_to_rank(smem_u32(&full_bar[0]), 0);
+            [[maybe_unused]] int trit = 0;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < a.num_tiles; tile += tstep) {
                 const int nt = tile % a.n_tiles;
                 for (int kb = 0; kb < KB; ++kb) {
+                    SDR_TR(2, trit, 0);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    SDR_TR(2, trit, 1);
+                    ++trit;
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 4 * bhalf);   // 2 CTAs x (hi + lo)
                     const int row = ((nt * KB + kb) * 2 + rank) * a.tile_n;              // first row of this CTA's box
                     tma_load_b_2d(b_base + (size_t)stage * kBStageBytes, &wmap,
@@ -665,16 +813,21 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
         if (lane == 0 && rank == 0) {
             const uint32_t idesc = umma_idesc_bf16(a.tile_n);
             uint32_t ti = 0;
+            [[maybe_unused]] int trit = 0;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < a.num_tiles; tile += tstep, ++ti) {
                 const int acc = ti & 1;
                 const uint32_t aphase = (ti >> 1) & 1;
+                SDR_TR(4, ti, 0);
                 mbar_wait_cluster(&tempty_bar[acc], aphase ^ 1);          // both CTAs' epilogues drained this accumulator
+                SDR_TR(4, ti, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxTileN;
                 for (int kb = 0; kb < KB; ++kb) {
+                    SDR_TR(3, trit, 0);
                     mbar_wait_cluster(&full_bar[stage], phase);           // A of both CTAs transformed, B of both landed
+                    SDR_TR(3, trit, 1);
                     tc_fence_after();
                     const uint32_t sa_hi = smem_u32(a_base + (size_t)stage * kAStageBytes);
                     const uint32_t sa_lo = sa_hi + kAHalf;
@@ -692,17 +845,21 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                         umma_bf16(d_tmem, dah, dbl, idesc, 1u);
                     }
                     umma_commit(&empty_bar[stage]);           // frees this stage in BOTH CTAs once these MMAs retire
+                    SDR_TR(3, trit, 2);
+                    ++trit;
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);                 // accumulator ready for both CTAs' epilogues
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < epi_warps(MODE)) {
         // ===================== epilogue: TMEM -> registers -> global =====================
-        const int q = warp;                 // TMEM lane quarter of this warp
+        constexpr int EG = epi_warps(MODE) / 4;   // warps per TMEM lane quarter; warp w owns columns [col0, col0 + tile_n / EG)
+        const int q = warp & 3;             // TMEM lane quarter of this warp
+        const int col0 = (warp >> 2) * (a.tile_n / EG);
         const size_t Ls = (size_t)a.L;
-        const int nchunks = a.tile_n / kEpiChunk;
+        const int nchunks = a.tile_n / kEpiChunk / EG;
         // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
         constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
         constexpr bool kGateTma = SDR_MMA_BULK && MODE == 2;    // gate tiles arrive through TMA loads into the staging ring
@@ -740,20 +897,35 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
             const int acc = ti & 1;
             const uint32_t aphase = (ti >> 1) & 1;
             const TileCoord tc = decode_tile(a, tile, rank);
-            float* const sb = s_bias + q * kMaxTileN;          // this warp's private copy of the tile's bias
-            const int ncols = min(a.tile_n, a.M - tc.n0);      // real output channels in this tile (< tile_n: padding)
-            __syncwarp();                                      // the warp is done with the previous tile's bias
-            for (int j = lane; j < a.tile_n; j += 32)
-                sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + j) : 0.f;
-            __syncwarp();
+            float* const sb = s_bias + warp * (kMaxTileN / EG);        // this warp's private copy of its columns' bias
+            const int ncols = min(a.tile_n, a.M - tc.n0) - col0;   // real output channels among this warp's columns (<= 0: padding)
+            if (ti == 0) {                                     // first tile: load the bias directly
+                for (int j = lane; j < a.tile_n / EG; j += 32)
+                    sb[j] = (a.bias && j < ncols) ? __ldg(a.bias + tc.n0 + col0 + j) : 0.f;
+                __syncwarp();
+            }
+            // the NEXT tile's bias travels in registers while this tile drains (it used to cost ~0.5 us of exposed
+            // L2 latency between two tiles)
+            constexpr int NB = kMaxTileN / EG / 32;
+            float nb[NB];
+            {
+                const int nxt = tile + tstep;
+                const int n0n = (nxt % a.n_tiles) * a.tile_n;
+                const int ncn = min(a.tile_n, a.M - n0n) - col0;
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    const int j = lane + 32 * r;
+                    nb[r] = (nxt < a.num_tiles && a.bias && j < ncn && j < a.tile_n / EG) ? __ldg(a.bias + n0n + col0 + j) : 0.f;
+                }
+            }
             const int l = tc.l0 + q * 32 + lane;
             const bool valid = l < a.L;
-            const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0) * Ls + l;       // (m = n0, l)
+            const size_t out_row0 = ((size_t)tc.sample * a.M + tc.n0 + col0) * Ls + l;   // (m = n0 + col0, l)
             // MODE 1: residual (may alias y: in-place skip connection); MODE 2: gate operand of this tile
             const float* ep = nullptr;
             if (MODE == 1) ep = a.residual + out_row0;
             if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
-            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN);
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN + col0);
             float st_s = 0.f, st_q = 0.f;
             if (MODE == 1 || (MODE == 2 && !kGateTma)) {  // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
@@ -825,7 +997,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                 // position: conflict-free rows) and leaves as ONE TMA tensor store (or fp32 reduce-add, for the
                 // in-place skip connection).  Nothing waits on global memory; the tensor map clips ragged
                 // position tiles and padded channels.  One 128-thread barrier per chunk; thread 0 issues.
+                if (warp == 0 && lane == 0) SDR_TR(5, ti, 0);
                 mbar_wait(&tfull_bar[acc], aphase);
+                if (warp == 0 && lane == 0) SDR_TR(5, ti, 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < nchunks; ++c) {
@@ -862,7 +1036,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                 // ahead, across tile boundaries), so no global load sits on the accumulator's way out.
                 const int nch = min(nchunks, (ncols + kEpiChunk - 1) / kEpiChunk);
                 float* yo = a.y + out_row0;
+                if (warp == 0 && lane == 0) SDR_TR(5, ti, 0);
                 mbar_wait(&tfull_bar[acc], aphase);
+                if (warp == 0 && lane == 0) SDR_TR(5, ti, 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c) {
@@ -907,7 +1083,9 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                 }
             } else {
                 issue_ex(EA, 0);
+                if (warp == 0 && lane == 0) SDR_TR(5, ti, 0);
                 mbar_wait(&tfull_bar[acc], aphase);
+                if (warp == 0 && lane == 0) SDR_TR(5, ti, 1);
                 tc_fence_after();
     #pragma unroll 1
                 for (int c = 0; c < nchunks; c += 2) {
@@ -920,6 +1098,11 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
             tc_fence_before();
             __syncwarp();                                  // every lane's tcgen05.ld of this accumulator has completed
             if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+            if (warp == 0 && lane == 0) SDR_TR(5, ti, 2);
+#pragma unroll
+            for (int r = 0; r < NB; ++r)                       // (the __syncwarp above ordered the last reads of sb)
+                if (lane + 32 * r < a.tile_n / EG) sb[lane + 32 * r] = nb[r];
+            __syncwarp();
             if (STATS) {
                 st_s = warp_sum(st_s);
                 st_q = warp_sum(st_q);
@@ -967,10 +1150,10 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
-constexpr size_t kMmaSmemBytes = (size_t)kStages * (kAStageBytes + kBStageBytes) +
+constexpr size_t kMmaSmemBytes = (size_t)kStages * (kAStageBytes + kBStageBytes) + (size_t)kRawStages * kRawStageBytes +
                                  kProdWarps * 64 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
                                  (size_t)kStgBufs * kStgFloats * sizeof(float) +
-                                 (2 * kStages + 4 + 2 * kStgBufs + 2) * sizeof(uint64_t);
+                                 (2 * kStages + 4 + 2 * kStgBufs + 4 + 2) * sizeof(uint64_t);
 static_assert(kEpiChunk == 16, "tmem_ld16 is hard-wired in the epilogue");
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
@@ -1022,6 +1205,23 @@ static int make_weight_map(CUtensorMap* tm, const void* wpk, size_t bytes, int t
     return r == CUDA_SUCCESS ? SDR_OK : SDR_ERR_UNSUPPORTED;
 }
 
+// Tensor map of the activations [samples][K][L] with a [1][64][128] box: one raw k-block tile of one CTA
+// (positions beyond L arrive as zeros: ragged last tiles and the idle CTA of an odd pair need no special case).
+static int make_act_map(CUtensorMap* tm, const float* x, int samples, int K, int L) {
+    memset(tm, 0, sizeof(*tm));
+    if (!SDR_MMA_RAW_TMA) return SDR_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return SDR_ERR_CUDA;
+    const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)K, (cuuint64_t)samples};
+    const cuuint64_t strides[2] = {(cuuint64_t)L * 4, (cuuint64_t)L * K * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kTileM, (cuuint32_t)kBlockK, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SDR_OK : SDR_ERR_UNSUPPORTED;
+}
+
 // Persistent launch as clusters of two CTAs (a CTA pair shares one TPC): as many pairs as can be resident at once
 // (queried once per kernel instantiation and device), never more than there are pair tiles.
 // (All instantiations share one function-pointer type, so the per-kernel state is keyed by the pointer, not by Kern.)
@@ -1030,7 +1230,8 @@ static std::mutex g_pair_mutex;
 static std::vector<PairLaunchInfo> g_pair_info;
 
 template <typename Kern>
-static int launch_pairs(Kern kern, const MmaArgs& a, const CUtensorMap& tmap, const CUtensorMap& wmap, cudaStream_t st) {
+static int launch_pairs(Kern kern, const MmaArgs& a, const CUtensorMap& tmap, const CUtensorMap& wmap, const CUtensorMap& xmap,
+                        cudaStream_t st) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return SDR_ERR_CUDA;
     cudaLaunchConfig_t cfg;
@@ -1066,9 +1267,16 @@ static int launch_pairs(Kern kern, const MmaArgs& a, const CUtensorMap& tmap, co
     }
     const int pairs = a.num_tiles < max_pairs ? a.num_tiles : max_pairs;
     cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
-    if (cudaLaunchKernelEx(&cfg, kern, a, tmap, wmap) != cudaSuccess) { cudaGetLastError(); return SDR_ERR_CUDA; }
+    if (cudaLaunchKernelEx(&cfg, kern, a, tmap, wmap, xmap) != cudaSuccess) { cudaGetLastError(); return SDR_ERR_CUDA; }
     return SDR_OK;
 }
+
+#if SDR_MMA_TRACE
+static long long* g_trace_buf = nullptr;
+extern "C" __attribute__((visibility("default"))) void sdr_debug_set_trace(void* device_buf) {
+    g_trace_buf = static_cast<long long*>(device_buf);
+}
+#endif
 
 int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, const float* bias,
                          const float* residual, const float* gate, int gate_channels,
@@ -1084,6 +1292,9 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     a.x = x; a.nin = nin; a.wpk = static_cast<const uint8_t*>(wpk); a.bias = bias; a.residual = residual;
     a.gate = gate; a.gate_channels = gate_channels; a.y = y; a.stats_out = stats_out;
     a.M = M; a.K = K; a.L = L; a.epilogue = epilogue;
+#if SDR_MMA_TRACE
+    a.trace = g_trace_buf;
+#endif
     a.win_k = 0; a.win_hop = 0; a.win_pad = 0; a.win_a = 0; a.win_T = 0;
     a.tile_n = mma_tile_n(M);
     a.n_tiles = mma_pad_m(M) / a.tile_n;
@@ -1102,10 +1313,11 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     CUtensorMap ymap;      // MODE 3: the in-place output; MODE 2: the gate tensor [samples][gate_channels][L]
     if (int rc = mode == 2 ? make_tile_map(&ymap, gate, samples, gate_channels, L, SDR_MMA_BULK)
                            : make_tile_map(&ymap, y, samples, M, L, mode == 3)) return rc;
-    CUtensorMap wmap;
+    CUtensorMap wmap, xmap;
     if (int rc = make_weight_map(&wmap, wpk, pointwise_mma_packed_bytes(M, K), a.tile_n)) return rc;
+    if (int rc = make_act_map(&xmap, x, samples, K, L)) return rc;
 #define SDR_MMA_CASE(A, MD, ST)                                                                                   \
-    if (act == A && mode == MD && stats == ST) return launch_pairs(pw_mma_kernel<false, A, MD, ST>, a, ymap, wmap, st);
+    if (act == A && mode == MD && stats == ST) return launch_pairs(pw_mma_kernel<false, A, MD, ST>, a, ymap, wmap, xmap, st);
     SDR_MMA_CASE(false, 0, false) SDR_MMA_CASE(false, 0, true)
     SDR_MMA_CASE(true, 0, false)  SDR_MMA_CASE(true, 0, true)
     SDR_MMA_CASE(false, 1, false) SDR_MMA_CASE(false, 1, true)
@@ -1144,6 +1356,9 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     a.wpk = static_cast<const uint8_t*>(wpk); a.bias = nullptr; a.residual = nullptr; a.gate = nullptr;
     a.gate_channels = 0; a.y = enc; a.stats_out = stats;
     a.M = N; a.K = enc_kpad(A, Kk); a.L = L; a.epilogue = 0;
+#if SDR_MMA_TRACE
+    a.trace = nullptr;
+#endif
     a.win_k = Kk; a.win_hop = Kk / 2; a.win_pad = Kk / 2; a.win_a = A; a.win_T = T;
     a.tile_n = mma_tile_n(N);
     a.n_tiles = mma_pad_m(N) / a.tile_n;
@@ -1156,8 +1371,10 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     CUtensorMap ymap, wmap;
     if (int rc = make_tile_map(&ymap, enc, B, N, L, false)) return rc;
     if (int rc = make_weight_map(&wmap, wpk, encoder_mma_packed_bytes(N, A, Kk), a.tile_n)) return rc;
-    if (stats) return launch_pairs(pw_mma_kernel<true, false, 0, true>, a, ymap, wmap, st);
-    return launch_pairs(pw_mma_kernel<true, false, 0, false>, a, ymap, wmap, st);
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));               // window mode gathers the waveform itself
+    if (stats) return launch_pairs(pw_mma_kernel<true, false, 0, true>, a, ymap, wmap, xmap, st);
+    return launch_pairs(pw_mma_kernel<true, false, 0, false>, a, ymap, wmap, xmap, st);
 }
 
 }  // namespace sdr

@@ -4,7 +4,7 @@ set -uo pipefail
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
-for lib in "" variants/pair_nolean.so variants/epi8_lean.so; do
+for lib in "" variants/pair_lean.so; do
   echo "=== ${lib:-product}"
   export SDR_B200_LIB=${lib:+$PWD/$lib}
   [ -z "$lib" ] && unset SDR_B200_LIB
