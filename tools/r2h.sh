@@ -3,7 +3,7 @@ set -uo pipefail
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
-  timeout -k 10 300 python -m pytest tests/test_gpu_stages.py -m gpu -q -p no:cacheprovider -k "tensor_core" 2>&1 | tail -3
+  timeout -k 10 300 python -m pytest tests/test_gpu_stages.py -m gpu -q -p no:cacheprovider -k "tensor_core or depthwise or merge" 2>&1 | tail -3
   timeout -k 10 400 python -m pytest tests/test_gpu_model.py -m gpu -q -p no:cacheprovider -k "golden or cfg2 or cfg3 or cfg5 or cfg4" 2>&1 | tail -3
   timeout -k 10 200 python tools/bench_stages.py --reps 7 --only tcgen05 2>&1 | grep kernel | python -c "
 import sys, json
@@ -16,6 +16,4 @@ import sys, json
 d = json.loads(sys.stdin.read()); print('bench $wl %.1f mixtures/s  %.3f ms/step  e2e %.1f  fwd_hbm %.3f per_block %.3f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['forward_hbm']['frac'], d['roofline']['per_block']['frac']))
 for k in d['roofline']['kernels']: print('    %-60s %.1f us %.3f' % (k['kernel'], k['avg_launch_ms']*1e3, k['frac']))"
   done
-  SDR_B200_LIB=$PWD/variants/trace.so SM_GHZ=1.9 timeout -k 10 200 python tools/trace_gemm.py 2>&1 > gpurun_out/r2h_trace.txt
-  grep -E "====|steady|epilogue warp" -A1 gpurun_out/r2h_trace.txt | cut -c1-400
 } 2>&1 | tee gpurun_out/r2h.txt
