@@ -20,6 +20,8 @@ int launch_overlap_add(const float*, const float*, const float2*, float*, int, i
 int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
+int launch_pointwise_small_preadd(const float*, const float*, const NormIn&, float*, const float*, const float*, float*,
+                                  double*, int, int, int, int, cudaStream_t);
 // pre/post steps (prepost.cu)
 int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
 int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
@@ -230,6 +232,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
         const int s0 = 1 + i * (D + 2 + (l.gc ? 1 : 0));
         const UBlockOff& u = l.ub[i];
         const float* bin = x;                       // block input == residual
+        bool proj_done = false;
         if (l.gc) {
             const TacOff& tc = l.tac[i];
             const float* tp[9];
@@ -237,12 +240,20 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
             double* st_tac = slot(s0 + D + 2);
             SDR_TRY(launch_tac(x, tp, o, st_tac, B, l.G, cob, L, st));
             NormIn tn{st_tac, pk + tc.g, pk + tc.be, nullptr, (double)cob * L};
-            SDR_TRY(launch_tac_apply(x, o, tn, xt, ns, cob, L, st));
             bin = xt;
+            // xt = x + GlobLN(o) is formed inside proj_1x1's operand load (and written once for the skip connection)
+            // when the streaming small-channel kernel takes the shape; otherwise it is materialised first
+            int fused = u.proj_pk ? SDR_ERR_UNSUPPORTED
+                                  : launch_pointwise_small_preadd(x, o, tn, xt, pk + u.proj_w, pk + u.proj_b, y, slot(s0),
+                                                                  ns, cib, cob, L, st);
+            if (fused != SDR_OK && fused != SDR_ERR_UNSUPPORTED) return fused;
+            if (fused != SDR_OK) SDR_TRY(launch_tac_apply(x, o, tn, xt, ns, cob, L, st));
+            else proj_done = true;
         }
         // proj_1x1: raw + stats
-        SDR_TRY(pointwise(bin, none, pk + u.proj_w, u.proj_pk ? pk + u.proj_pk : nullptr, pk + u.proj_b,
-                          nullptr, nullptr, 0, y, slot(s0), ns, cib, cob, L, 0, st));
+        if (!proj_done)
+            SDR_TRY(pointwise(bin, none, pk + u.proj_w, u.proj_pk ? pk + u.proj_pk : nullptr, pk + u.proj_b,
+                              nullptr, nullptr, 0, y, slot(s0), ns, cib, cob, L, 0, st));
         // level 0: PReLU(GLN(proj)) on load
         {
             NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)cib * L};
@@ -396,8 +407,10 @@ int sdr_forward(const sdr_config* cfg, const void* packed, const float* mixture,
 int sdr_forward_launch_count(const sdr_config* cfg) {
     const Layout l = make_layout(cfg);
     if (!l.ok) return SDR_ERR_BAD_CONFIG;
-    // encoder + bottleneck + U * (proj + D depthwise + merge + res [+ tac + tac_apply]) + mask + decoder GEMM + overlap-add
-    return 2 + l.U * (l.D + 3 + (l.gc ? 2 : 0)) + 3;
+    // encoder + bottleneck + U * (proj + D depthwise + merge + res [+ tac (+ tac_apply unless it is folded into proj)])
+    // + mask + decoder GEMM + overlap-add
+    const bool folded = l.gc && l.U > 0 && !l.ub[0].proj_pk && l.cob <= 64 && l.cib <= 64 && l.D >= 2;   // L % 4 == 0 then
+    return 2 + l.U * (l.D + 3 + (l.gc ? (folded ? 1 : 2) : 0)) + 3;
 }
 
 size_t sdr_host_staging_bytes(const sdr_config* cfg, int B, int64_t T) {

@@ -28,6 +28,11 @@ struct PwArgs {
     int M, K, L;
     int l_tiles;
     int epilogue;      // 0 plain, 1 relu(y) * gate
+    // small-channel kernel only (GroupComm, groupcomm_sudormrf_v2.py:381-383,411): the operand is
+    // x + GlobLN(pre_add) (the TAC residual + norm), which is also written to pre_out (the block's skip connection)
+    const float* pre_add;
+    NormIn pre_norm;
+    float* pre_out;
 };
 
 constexpr int kPwThreads = 256;
@@ -202,21 +207,28 @@ pw_gemm_kernel(const PwArgs a) {
 // warp), 64 FMAs against 16 weights broadcast from shared memory, float4 stores.
 // Requires K <= 64, L % 4 == 0.
 // ---------------------------------------------------------------------------
-constexpr int kSmThreads = 256;
+constexpr int kSmMaxThreads = 256;
 constexpr int kSmMT = 16;          // output channels per thread
+constexpr int kSmKT = 8;           // input rows whose loads are issued together (8 x 16 B in flight per thread)
 constexpr int kSmMaxK = 64;
 
-__global__ void __launch_bounds__(kSmThreads)
+// The launch list of the GroupComm model (profiles/r02_groupcomm.md) had this kernel at 0.34 of the HBM roofline: the
+// block size did not divide the 800 position quads of a row (a quarter of the threads idle) and only 4 loads per thread
+// were in flight.  Now: block size chosen by the launcher to divide the row, loads batched 8 rows at a time.
+template <bool PRE>                     // PRE: operand = x + GlobLN(pre_add), written to pre_out (GroupComm proj_1x1)
+__global__ void __launch_bounds__(kSmMaxThreads, 2)
 pw_small_kernel(const PwArgs a, int chunks_per_sample) {
+    constexpr int KT = PRE ? kSmKT / 2 : kSmKT;            // rows per batch: 4 + 4 loads in flight with the second operand
     __shared__ __align__(16) float sW[kSmMaxK][kSmMT];     // [k][m]
     __shared__ float2 sAB[kSmMaxK];                         // folded norm: y = x*a + b
+    __shared__ float2 sPre[kSmMaxK];                        // folded norm of the pre-add operand
     __shared__ float sBias[kSmMT];
     __shared__ float s_red[64];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int sample = blockIdx.x / chunks_per_sample;
     const int chunk = blockIdx.x - sample * chunks_per_sample;
     const int m0 = blockIdx.y * kSmMT;
-    for (int i = tid; i < a.K * kSmMT; i += kSmThreads) {
+    for (int i = tid; i < a.K * kSmMT; i += nthr) {
         const int k = i / kSmMT, m = i - k * kSmMT;
         sW[k][m] = (m0 + m < a.M) ? __ldg(a.W + (size_t)(m0 + m) * a.K + k) : 0.f;
     }
@@ -229,39 +241,72 @@ pw_small_kernel(const PwArgs a, int chunks_per_sample) {
             bb = fmaf(-sn.mean, aa, __ldg(a.nin.beta + tid));
         }
         sAB[tid] = make_float2(aa, bb);
+        float pa = 1.f, pb = 0.f;
+        if (PRE && a.pre_norm.stats) {
+            const SampleNorm sn = sample_norm(a.pre_norm, sample);
+            pa = __ldg(a.pre_norm.gamma + tid) * sn.rstd;
+            pb = fmaf(-sn.mean, pa, __ldg(a.pre_norm.beta + tid));
+        }
+        sPre[tid] = make_float2(pa, pb);
     }
     const bool act = a.nin.prelu != nullptr;
     const float slope = act ? __ldg(a.nin.prelu) : 1.f;
     __syncthreads();
 
     const int QR = a.L >> 2;
-    const int q = chunk * kSmThreads + tid;
+    const int q = chunk * nthr + tid;
     float st_s = 0.f, st_q = 0.f;
     if (q < QR) {
         const float* xp = a.x + (size_t)sample * a.K * a.L + 4 * q;
         float acc[kSmMT][4];
 #pragma unroll
         for (int m = 0; m < kSmMT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = sBias[m]; }
-#pragma unroll 4
-        for (int k = 0; k < a.K; ++k) {
-            float4 v = ldg4(xp + (size_t)k * a.L);
-            const float2 ab = sAB[k];
-            v.x = fmaf(v.x, ab.x, ab.y); v.y = fmaf(v.y, ab.x, ab.y);
-            v.z = fmaf(v.z, ab.x, ab.y); v.w = fmaf(v.w, ab.x, ab.y);
-            if (act) {
-                v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope;
-                v.z = v.z >= 0.f ? v.z : v.z * slope; v.w = v.w >= 0.f ? v.w : v.w * slope;
+#pragma unroll 1
+        for (int k0 = 0; k0 < a.K; k0 += KT) {
+            float4 v[KT];
+#pragma unroll
+            for (int j = 0; j < KT; ++j)                       // all loads of the batch first
+                v[j] = (k0 + j < a.K) ? ldg4(xp + (size_t)(k0 + j) * a.L) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (PRE) {                               // operand = x + GlobLN(pre_add); kept for the skip connection
+                const float* pp = a.pre_add + (size_t)sample * a.K * a.L + 4 * q;
+                float4 w[KT];
+#pragma unroll
+                for (int j = 0; j < KT; ++j)
+                    w[j] = (k0 + j < a.K) ? ldg4(pp + (size_t)(k0 + j) * a.L) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    if (k0 + j < a.K) {
+                        const float2 pn = sPre[k0 + j];
+                        v[j].x += fmaf(w[j].x, pn.x, pn.y); v[j].y += fmaf(w[j].y, pn.x, pn.y);
+                        v[j].z += fmaf(w[j].z, pn.x, pn.y); v[j].w += fmaf(w[j].w, pn.x, pn.y);
+                        if (blockIdx.y == 0)
+                            *reinterpret_cast<float4*>(a.pre_out + ((size_t)sample * a.K + k0 + j) * a.L + 4 * q) = v[j];
+                    }
+                }
             }
 #pragma unroll
-            for (int m4 = 0; m4 < kSmMT / 4; ++m4) {
-                const float4 w = *reinterpret_cast<const float4*>(&sW[k][m4 * 4]);
-                const float ww[4] = {w.x, w.y, w.z, w.w};
+            for (int j = 0; j < KT; ++j) {
+                if (k0 + j < a.K) {
+                    const float2 ab = sAB[k0 + j];
+                    float4 x = v[j];
+                    x.x = fmaf(x.x, ab.x, ab.y); x.y = fmaf(x.y, ab.x, ab.y);
+                    x.z = fmaf(x.z, ab.x, ab.y); x.w = fmaf(x.w, ab.x, ab.y);
+                    if (act) {
+                        x.x = x.x >= 0.f ? x.x : x.x * slope; x.y = x.y >= 0.f ? x.y : x.y * slope;
+                        x.z = x.z >= 0.f ? x.z : x.z * slope; x.w = x.w >= 0.f ? x.w : x.w * slope;
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    acc[m4 * 4 + u][0] = fmaf(ww[u], v.x, acc[m4 * 4 + u][0]);
-                    acc[m4 * 4 + u][1] = fmaf(ww[u], v.y, acc[m4 * 4 + u][1]);
-                    acc[m4 * 4 + u][2] = fmaf(ww[u], v.z, acc[m4 * 4 + u][2]);
-                    acc[m4 * 4 + u][3] = fmaf(ww[u], v.w, acc[m4 * 4 + u][3]);
+                    for (int m4 = 0; m4 < kSmMT / 4; ++m4) {
+                        const float4 w = *reinterpret_cast<const float4*>(&sW[k0 + j][m4 * 4]);
+                        const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            acc[m4 * 4 + u][0] = fmaf(ww[u], x.x, acc[m4 * 4 + u][0]);
+                            acc[m4 * 4 + u][1] = fmaf(ww[u], x.y, acc[m4 * 4 + u][1]);
+                            acc[m4 * 4 + u][2] = fmaf(ww[u], x.z, acc[m4 * 4 + u][2]);
+                            acc[m4 * 4 + u][3] = fmaf(ww[u], x.w, acc[m4 * 4 + u][3]);
+                        }
+                    }
                 }
             }
         }
@@ -288,6 +333,17 @@ pw_small_kernel(const PwArgs a, int chunks_per_sample) {
     if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
 }
 
+// block size for rows of `quads` position quads: the multiple of 32 in [128, 256] that wastes the fewest threads
+static int small_block_threads(int quads) {
+    int best = kSmMaxThreads;
+    long long best_waste = -1;
+    for (int t = kSmMaxThreads; t >= 128; t -= 32) {
+        const long long waste = (long long)((quads + t - 1) / t) * t - quads;
+        if (best_waste < 0 || waste < best_waste) { best = t; best_waste = waste; }
+    }
+    return best;
+}
+
 template <int BM>
 static int launch_bm(const PwArgs& a, int samples, bool vec, cudaStream_t st) {
     const long long gx = (long long)a.l_tiles * samples;
@@ -309,21 +365,46 @@ int launch_pointwise_ffma(const float* x, const NormIn& nin, const float* W, con
     a.x = x; a.nin = nin; a.W = W; a.bias = bias; a.residual = residual; a.gate = gate;
     a.gate_channels = gate_channels; a.y = y; a.stats_out = stats_out;
     a.M = M; a.K = K; a.L = L; a.l_tiles = (L + kBN - 1) / kBN; a.epilogue = epilogue;
+    a.pre_add = nullptr; a.pre_norm = NormIn{nullptr, nullptr, nullptr, nullptr, 1.0}; a.pre_out = nullptr;
     uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y);
     if (residual) al |= reinterpret_cast<uintptr_t>(residual);
     if (gate) al |= reinterpret_cast<uintptr_t>(gate);
     const bool vec = (L % 4 == 0) && (al % 16 == 0);
     if (vec && K <= kSmMaxK && M <= 64) {                 // streaming small-channel kernel
-        const int chunks = (L / 4 + kSmThreads - 1) / kSmThreads;
+        const int threads = small_block_threads(L / 4);
+        const int chunks = (L / 4 + threads - 1) / threads;
         const long long gx = (long long)chunks * samples;
         if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
         dim3 grid((unsigned)gx, (unsigned)((M + kSmMT - 1) / kSmMT));
-        pw_small_kernel<<<grid, kSmThreads, 0, st>>>(a, chunks);
+        pw_small_kernel<false><<<grid, threads, 0, st>>>(a, chunks);
         return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
     }
     if (M > 64) return launch_bm<128>(a, samples, vec, st);
     if (M > 32) return launch_bm<64>(a, samples, vec, st);
     return launch_bm<32>(a, samples, vec, st);
+}
+
+// 1x1 conv of x + GlobLN(pre_add) for the small-channel (GroupComm) blocks; xt_out receives x + GlobLN(pre_add).
+// SDR_ERR_UNSUPPORTED when the streaming kernel cannot take the shape (the caller then materialises xt first).
+int launch_pointwise_small_preadd(const float* x, const float* pre_add, const NormIn& pre_norm, float* xt_out,
+                                  const float* W, const float* bias, float* y, double* stats_out,
+                                  int samples, int M, int K, int L, cudaStream_t st) {
+    if (samples <= 0 || M <= 0 || K <= 0 || L <= 0 || !x || !pre_add || !xt_out || !W || !y) return SDR_ERR_BAD_ARGUMENT;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                         reinterpret_cast<uintptr_t>(pre_add) | reinterpret_cast<uintptr_t>(xt_out);
+    if ((L % 4) != 0 || (al % 16) != 0 || K > kSmMaxK || M > 64) return SDR_ERR_UNSUPPORTED;
+    PwArgs a;
+    a.x = x; a.nin = NormIn{nullptr, nullptr, nullptr, nullptr, 1.0}; a.W = W; a.bias = bias; a.residual = nullptr;
+    a.gate = nullptr; a.gate_channels = 0; a.y = y; a.stats_out = stats_out;
+    a.M = M; a.K = K; a.L = L; a.l_tiles = (L + kBN - 1) / kBN; a.epilogue = 0;
+    a.pre_add = pre_add; a.pre_norm = pre_norm; a.pre_out = xt_out;
+    const int threads = small_block_threads(L / 4);
+    const int chunks = (L / 4 + threads - 1) / threads;
+    const long long gx = (long long)chunks * samples;
+    if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)gx, (unsigned)((M + kSmMT - 1) / kSmMT));
+    pw_small_kernel<true><<<grid, threads, 0, st>>>(a, chunks);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
 }  // namespace sdr

@@ -248,7 +248,7 @@ def test_overlap_add(B, SA, K, L, T, mc):
 
 
 @pytest.mark.parametrize("B,G,n,L", [(2, 16, 16, 3200), (2, 4, 8, 100), (3, 8, 4, 33),
-                                     (1, 2, 32, 40), (2, 16, 16, 31)])
+                                     (1, 2, 32, 40), (2, 16, 16, 31), (3, 8, 16, 200), (1, 5, 16, 16)])
 def test_tac(B, G, n, L):
     g = torch.Generator().manual_seed(5)
     H = 3 * n
@@ -268,8 +268,9 @@ def test_tac(B, G, n, L):
     taps = {}
     O.tac(x, sd, "", taps)
     want = taps["TAC_output"]
-    close(o, want)
-    check_stats(st, want.reshape(B * G, n, L))
+    # n = 16 runs on tensor cores (three chained bf16x3 GEMMs: ~3e-5); the other group widths are exact-fp32 FFMA
+    close(o, want, tol=1e-4 if n == 16 else 2e-5)
+    check_stats(st, want.reshape(B * G, n, L), rtol=1e-4 if n == 16 else 1e-5)
 
 
 @pytest.mark.parametrize("kind", ["uniform", "magsq"])
