@@ -57,12 +57,14 @@ constexpr int kAHalf = kTileM * 128;   // 16 KB: bf16 [128 rows][64 k]
 constexpr int kBHalfMax = (kMaxTileN / 2) * 128;             // 16 KB: this CTA's tile_n / 2 weight rows, one bf16 image
 constexpr int kAStageBytes = 2 * kAHalf;                     // 32 KB: hi + lo
 constexpr int kBStageBytes = 2 * kBHalfMax;                  // 32 KB: hi + lo
-// Warp roles: [0, 8) epilogue slots (the plain-store exit, MODE 0, uses all 8: two warps per TMEM lane quarter, each
-// owning half of the tile's columns; the staged exits, MODE 2 / 3, and MODE 1 use the first 4), 8 MMA issuer,
+// Warp roles: [0, 8) epilogue slots (the register exits, MODE 0 / 2, use all 8: two warps per TMEM lane quarter, each
+// owning half of the tile's columns; the staged in-place exit, MODE 3, and MODE 1 use the first 4), 8 MMA issuer,
 // 9 weight TMA, [10, 18) operand transform, 18 raw activation TMA.  The role timeline (tools/trace_gemm.py) showed
 // proj bound by its 4 epilogue warps: 4.1 us to drain a tile + 0.8 us between tiles against 4.0 us of MMA time.
 constexpr int kEpiSlots = 8, kEpiWarps = 4, kMmaWarp = 8, kTmaWarp = 9, kProdWarp0 = 10, kProdWarps = 8;
-constexpr int epi_warps(int mode) { return mode == 0 ? 8 : 4; }
+// (MODE 2, ReLU x gate: 8 warps with the gate rows prefetched into registers a chunk ahead measured 184 us against
+// 257 us for 4 warps fed by a TMA gate-tile ring at the cfg-2 mask shape.)
+constexpr int epi_warps(int mode) { return (mode == 0 || mode == 2) ? 8 : 4; }
 constexpr int kRawWarp = kProdWarp0 + kProdWarps;             // 18: raw activation tile TMA producer (SDR_MMA_RAW_TMA)
 constexpr int kMmaThreads = 32 * (kProdWarp0 + kProdWarps + (SDR_MMA_RAW_TMA ? 1 : 0));   // 608 (576 without the raw loader)
 #define SDR_MMA_THREADS(MODE) kMmaThreads
@@ -352,7 +354,7 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile, int
 //   STATS:  accumulate (sum, sumsq) of the output
 template <bool WINDOW, bool ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(SDR_MMA_THREADS(MODE), 1)
-pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      // tmap: MODE 3 output, MODE 2 gate
+pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      // tmap: MODE 3 in-place output
               const __grid_constant__ CUtensorMap wmap,                       // wmap: packed weights as [rows][128 B]
               const __grid_constant__ CUtensorMap xmap) {                     // xmap: activations [samples][K][L], box [64][128]
     // 3 x (32 KB A stage + 32 KB B stage) + 8 KB of tables + 24 KB of epilogue staging + barriers
@@ -377,9 +379,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
     uint64_t* empty_bar = full_bar + kStages;        // [kStages]
     uint64_t* tfull_bar = empty_bar + kStages;       // [2]
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-    uint64_t* gfull_bar = tempty_bar + 2;            // [kStgBufs]  gate tile landed (TMA tx bytes); CTA-local
-    uint64_t* gempty_bar = gfull_bar + kStgBufs;     // [kStgBufs]  all 128 epilogue threads have read it; CTA-local
-    uint64_t* rfull_bar = gempty_bar + kStgBufs;     // [kRawStages] raw tile landed (TMA tx bytes); CTA-local
+    uint64_t* rfull_bar = tempty_bar + 2;            // [kRawStages] raw tile landed (TMA tx bytes); CTA-local
     uint64_t* rempty_bar = rfull_bar + 2;            // [kRawStages] all 8 transform warps hold it in registers; CTA-local
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(rempty_bar + 2);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -395,7 +395,6 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
     if (warp == kTmaWarp && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2 * kProdWarps + 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * epi_warps(MODE)); }
-        for (int s = 0; s < kStgBufs; ++s) { mbar_init(&gfull_bar[s], 1); mbar_init(&gempty_bar[s], kEpiWarps * 32); }
         for (int s = 0; s < 2; ++s) { mbar_init(&rfull_bar[s], 1); mbar_init(&rempty_bar[s], kProdWarps); }
         fence_barrier_init();
     }
@@ -862,33 +861,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
         const int nchunks = a.tile_n / kEpiChunk / EG;
         // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
         constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
-        constexpr bool kGateTma = SDR_MMA_BULK && MODE == 2;    // gate tiles arrive through TMA loads into the staging ring
-        int stg_i = 0;
-        uint32_t stg_k = 0;                  // how often the ring wrapped (mbarrier phase of the gate tiles)
-        // MODE 2: thread 0 runs a cursor over this CTA's (tile, chunk) sequence two chunks ahead of the consumers
-        struct GateCur { int tile, c, nch, b; uint32_t k; TileCoord tc; } gcur{};
-        auto gate_nch = [&](const TileCoord& t) { return min(nchunks, (min(a.tile_n, a.M - t.n0) + kEpiChunk - 1) / kEpiChunk); };
-        auto gate_issue = [&]() {
-            if (gcur.tile >= a.num_tiles) return;
-            if (gcur.k > 0) mbar_wait(&gempty_bar[gcur.b], (gcur.k - 1) & 1);    // its previous content has been read
-            mbar_arrive_expect_tx(&gfull_bar[gcur.b], kStgFloats * sizeof(float));
-            tma_load_3d(s_stage + gcur.b * kStgFloats, &tmap, &gfull_bar[gcur.b], gcur.tc.l0,
-                        (gcur.tc.n0 % a.gate_channels) + gcur.c * kEpiChunk, gcur.tc.sample);
-            if (++gcur.b == kStgBufs) { gcur.b = 0; ++gcur.k; }
-            if (++gcur.c == gcur.nch) {
-                gcur.c = 0;
-                gcur.tile += tstep;
-                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile, rank); gcur.nch = gate_nch(gcur.tc); }
-            }
-        };
-        if constexpr (kGateTma) {
-            if (tid == 0) {
-                gcur.tile = tile0;
-                if (gcur.tile < a.num_tiles) { gcur.tc = decode_tile(a, gcur.tile, rank); gcur.nch = gate_nch(gcur.tc); }
-                gate_issue();
-                gate_issue();
-            }
-        }
+        int stg_i = 0;                       // staging ring cursor (MODE 3)
         const uint32_t tempty_leader0 = map_to_rank(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = map_to_rank(smem_u32(&tempty_bar[1]), 0);
         uint32_t ti = 0;
@@ -924,10 +897,10 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
             // MODE 1: residual (may alias y: in-place skip connection); MODE 2: gate operand of this tile
             const float* ep = nullptr;
             if (MODE == 1) ep = a.residual + out_row0;
-            if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels)) * Ls + l;
+            if (MODE == 2) ep = a.gate + ((size_t)tc.sample * a.gate_channels + (tc.n0 % a.gate_channels) + col0) * Ls + l;
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxTileN + col0);
             float st_s = 0.f, st_q = 0.f;
-            if (MODE == 1 || (MODE == 2 && !kGateTma)) {  // pull this tile's residual / gate rows into L2 while the main loop runs
+            if (MODE == 1 || MODE == 2) {  // pull this tile's residual / gate rows into L2 while the main loop runs
                 const int lq = tc.l0 + q * 32;
                 if (lq < a.L) {
                     const float* e0 = ep - lane;               // position lq of row 0
@@ -1031,56 +1004,6 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                         bulk_commit();
                     }
                 }
-            } else if constexpr (kGateTma) {
-                // ReLU * gate: the gate rows of a chunk were fetched by TMA into the staging ring (two chunks
-                // ahead, across tile boundaries), so no global load sits on the accumulator's way out.
-                const int nch = min(nchunks, (ncols + kEpiChunk - 1) / kEpiChunk);
-                float* yo = a.y + out_row0;
-                if (warp == 0 && lane == 0) SDR_TR(5, ti, 0);
-                mbar_wait(&tfull_bar[acc], aphase);
-                if (warp == 0 && lane == 0) SDR_TR(5, ti, 1);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < nch; ++c) {
-                    if (tid == 0) gate_issue();                    // chunk (this + 2)
-                    tmem_ld16(t_acc + (uint32_t)(c * kEpiChunk), R);
-                    const float* gp = s_stage + stg_i * kStgFloats + q * 32 + lane;
-                    mbar_wait(&gfull_bar[stg_i], stg_k & 1);
-                    float E[kEpiChunk];
-#pragma unroll
-                    for (int j = 0; j < kEpiChunk; ++j) E[j] = gp[j * 128];
-                    mbar_arrive(&gempty_bar[stg_i]);
-                    if (++stg_i == kStgBufs) { stg_i = 0; ++stg_k; }
-                    const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiChunk);
-                    const int jmax = ncols - c * kEpiChunk;
-                    tmem_ld_wait();
-                    if (valid) {
-                        if (jmax >= kEpiChunk) {
-#pragma unroll
-                            for (int j4 = 0; j4 < kEpiChunk / 4; ++j4) {
-                                const float4 bv = b4[j4];
-                                const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const int j = j4 * 4 + u;
-                                    const float o = fmaxf(__uint_as_float(R[j]) + bb[u], 0.f) * E[j];
-                                    *yo = o;
-                                    yo += Ls;
-                                    if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < kEpiChunk; ++j) {
-                                if (j < jmax) {
-                                    const float o = fmaxf(__uint_as_float(R[j]) + sb[c * kEpiChunk + j], 0.f) * E[j];
-                                    yo[(size_t)j * Ls] = o;
-                                    if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
-                                }
-                            }
-                        }
-                    }
-                }
             } else {
                 issue_ex(EA, 0);
                 if (warp == 0 && lane == 0) SDR_TR(5, ti, 0);
@@ -1153,7 +1076,7 @@ int pack_pointwise_mma(const float* W, int M, int K, void* packed, cudaStream_t 
 constexpr size_t kMmaSmemBytes = (size_t)kStages * (kAStageBytes + kBStageBytes) + (size_t)kRawStages * kRawStageBytes +
                                  kProdWarps * 64 * sizeof(float2) + kEpiWarps * kMaxTileN * sizeof(float) +
                                  (size_t)kStgBufs * kStgFloats * sizeof(float) +
-                                 (2 * kStages + 4 + 2 * kStgBufs + 4 + 2) * sizeof(uint64_t);
+                                 (2 * kStages + 4 + 4 + 2) * sizeof(uint64_t);
 static_assert(kEpiChunk == 16, "tmem_ld16 is hard-wired in the epilogue");
 static_assert(kMmaSmemBytes <= 232448, "exceeds the 227 KB a CTA may own on sm_100");
 
@@ -1309,10 +1232,8 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     const bool inplace = SDR_MMA_BULK && residual == y && (reinterpret_cast<uintptr_t>(y) % 16) == 0;
     const int mode = epilogue == 1 ? 2 : (residual ? (inplace ? 3 : 1) : 0);
     const bool stats = stats_out != nullptr;
-    if (SDR_MMA_BULK && mode == 2 && (reinterpret_cast<uintptr_t>(gate) % 16) != 0) return SDR_ERR_UNSUPPORTED;   // TMA address
-    CUtensorMap ymap;      // MODE 3: the in-place output; MODE 2: the gate tensor [samples][gate_channels][L]
-    if (int rc = mode == 2 ? make_tile_map(&ymap, gate, samples, gate_channels, L, SDR_MMA_BULK)
-                           : make_tile_map(&ymap, y, samples, M, L, mode == 3)) return rc;
+    CUtensorMap ymap;      // MODE 3: the in-place output
+    if (int rc = make_tile_map(&ymap, y, samples, M, L, mode == 3)) return rc;
     CUtensorMap wmap, xmap;
     if (int rc = make_weight_map(&wmap, wpk, pointwise_mma_packed_bytes(M, K), a.tile_n)) return rc;
     if (int rc = make_act_map(&xmap, x, samples, K, L)) return rc;
