@@ -244,7 +244,7 @@ def run_b200(args, w, wl_name):
         from sudo_rm_rf_b200 import sharding
         sharding.broadcast_parameters(model, src=0)
     cfg = _engine.make_config(model)
-    launches_per_step = _native.lib().sdr_forward_launch_count(C.byref(cfg))
+    launches_per_step = _native.lib().sdr_forward_launch_count_at(C.byref(cfg), w["T"])
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_x = torch.rand(B, 1, T, generator=g).pin_memory()      # the reference's bench input (notebook :128)
@@ -439,26 +439,43 @@ def block_launchers(w, B, dev, stream):
     keep.append(none)
     n_, f_ = gemm("proj_1x1", x, none, Ci, Co, None, y, st[0])
     out.append((n_, f_, 4 * L * S * (Co + Ci), 2.0 * Co * Ci * L * S))
-    # depthwise levels (producer's GlobLN (+PReLU for level 0) applied on load)
-    for d in range(D):
-        src = y if d == 0 else z[d - 1]
-        Lin = L if d == 0 else L >> (d - 1)
-        nin = N.SdrNormIn(st[d].data_ptr(), ones.data_ptr(), zeros.data_ptr(), slope.data_ptr() if d == 0 else 0,
-                          float(Ci * Lin))
-        w5, b5 = rn(Ci, 5), rn(Ci)
-        keep.extend([nin, w5, b5])
-        stride = 1 if d == 0 else 2
-        out.append((f"depthwise level {d} (stride {stride})",
-                    (lambda src=src, nin=nin, w5=w5, b5=b5, d=d, Lin=Lin, stride=stride: N.check(lib.sdr_depthwise(
-                        P(src), C.byref(nin), P(w5), P(b5), P(z[d]), P(st[d + 1]), S, Ci, Lin, stride, sp))),
-                    4 * S * Ci * (Lin + (L >> d)), 10.0 * Ci * (L >> d) * S))
-    # merge (m reuses y's storage, as in the forward)
-    fins = (N.SdrNormIn * D)(*[N.SdrNormIn(st[d + 1].data_ptr(), ones.data_ptr(), zeros.data_ptr(), 0,
-                                           float(Ci * (L >> d))) for d in range(D)])
-    zp = (C.c_void_p * D)(*[t.data_ptr() for t in z])
-    keep.extend([fins, zp])
-    out.append(("merge", lambda: N.check(lib.sdr_merge(zp, fins, D, P(y), P(st[D + 1]), S, Ci, L, sp)),
-                4 * S * Ci * (L + sum(L >> d for d in range(D))), 3.0 * D * Ci * L * S))
+    arrD = lambda ts: (C.c_void_p * D)(*[t.data_ptr() for t in ts])
+    w5s, b5s = [rn(Ci, 5) for _ in range(D)], [rn(Ci) for _ in range(D)]
+    keep.extend([w5s, b5s])
+    nin0 = N.SdrNormIn(st[0].data_ptr(), ones.data_ptr(), zeros.data_ptr(), slope.data_ptr(), float(Ci * L))
+    keep.append(nin0)
+    scratch_bytes = lib.sdr_pyramid_scratch_bytes(S, Ci, D, L)
+    level_bytes = 4 * S * Ci * (2 * L + sum((L >> (d - 1)) + (L >> d) for d in range(1, D)))
+    merge_bytes = 4 * S * Ci * (L + sum(L >> d for d in range(D)))
+    if scratch_bytes:
+        # the forward's path at this shape: every depthwise level in ONE pass over y, then the affine merge
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        wa, ba, ga, bea, za = arrD(w5s), arrD(b5s), arrD([ones] * D), arrD([zeros] * D), arrD(z)
+        keep.extend([scratch, wa, ba, ga, bea, za])
+        out.append((f"depthwise pyramid, levels 0..{D - 1} in one pass (+ GlobLN solve)",
+                    lambda: N.check(lib.sdr_depthwise_pyramid(P(y), C.byref(nin0), wa, ba, ga, bea, za, P(st[1]), P(scratch),
+                                                              D, S, Ci, L, sp)),
+                    level_bytes, 10.0 * Ci * S * sum(L >> d for d in range(D))))
+        out.append(("merge (affine in the raw levels)",
+                    lambda: N.check(lib.sdr_merge_pyramid(za, P(scratch), D, P(y), P(st[D + 1]), S, Ci, L, sp)),
+                    merge_bytes, 3.0 * D * Ci * L * S))
+    else:
+        for d in range(D):
+            src = y if d == 0 else z[d - 1]
+            Lin = L if d == 0 else L >> (d - 1)
+            nin = nin0 if d == 0 else N.SdrNormIn(st[d].data_ptr(), ones.data_ptr(), zeros.data_ptr(), 0, float(Ci * Lin))
+            keep.append(nin)
+            stride = 1 if d == 0 else 2
+            out.append((f"depthwise level {d} (stride {stride})",
+                        (lambda src=src, nin=nin, d=d, Lin=Lin, stride=stride: N.check(lib.sdr_depthwise(
+                            P(src), C.byref(nin), P(w5s[d]), P(b5s[d]), P(z[d]), P(st[d + 1]), S, Ci, Lin, stride, sp))),
+                        4 * S * Ci * (Lin + (L >> d)), 10.0 * Ci * (L >> d) * S))
+        fins = (N.SdrNormIn * D)(*[N.SdrNormIn(st[d + 1].data_ptr(), ones.data_ptr(), zeros.data_ptr(), 0,
+                                               float(Ci * (L >> d))) for d in range(D)])
+        zp = arrD(z)
+        keep.extend([fins, zp])
+        out.append(("merge", lambda: N.check(lib.sdr_merge(zp, fins, D, P(y), P(st[D + 1]), S, Ci, L, sp)),
+                    merge_bytes, 3.0 * D * Ci * L * S))
     # res_conv + in-place skip connection
     nf = N.SdrNormIn(st[D + 1].data_ptr(), ones.data_ptr(), zeros.data_ptr(), slope.data_ptr(), float(Ci * L))
     keep.append(nf)
@@ -469,6 +486,11 @@ def block_launchers(w, B, dev, stream):
         for t in st:
             t.zero_()
     return out, reset, keep
+
+
+# NOTE on `algorithmic_bytes`: every figure follows SURVEY.md section 8(d) (each level's input read and output written
+# once, merge reading every level), also for the one-pass pyramid, which really moves fewer bytes (y + z_0 + R_d once):
+# its `frac` can therefore exceed what a level-by-level schedule could reach at the copy peak.
 
 
 def time_block(w, B, stream, flush, dev, reps=7):

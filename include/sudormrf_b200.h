@@ -93,8 +93,10 @@ int sdr_forward(const sdr_config* cfg, const void* packed,
                 int apply_mixture_consistency,
                 void* workspace, size_t workspace_bytes, sdr_stream stream);
 
-/* Number of kernels one sdr_forward enqueues (the benchmark's gpu_launches claim). */
+/* Number of kernels one sdr_forward enqueues (the benchmark's gpu_launches claim): for T = 32000 samples, and for
+ * any length (the depthwise levels run as one pass or level by level depending on the padded length).          */
 int sdr_forward_launch_count(const sdr_config* cfg);
+int sdr_forward_launch_count_at(const sdr_config* cfg, int64_t T);
 
 /* Same call with HOST buffers (pinned for real asynchrony): H2D copy of the
  * mixture, forward, D2H copy of the estimates, all on `stream`.  `dev_io` is a
@@ -170,6 +172,22 @@ int sdr_pointwise_mma(const float* x, const sdr_norm_in* fin, const void* packed
 int sdr_depthwise(const float* x, const sdr_norm_in* fin, const float* w5, const float* bias,
                   float* y, double* stats_out,
                   int samples, int C, int Lin, int stride, sdr_stream stream);
+
+/* The whole depthwise pyramid of a U-ConvBlock (improved_sudormrf.py:205-216) in one pass over the projection
+ * output y [samples,C,L] (fin: its GlobLN + PReLU).  Levels d >= 1 are affine in their inputs, so the kernel
+ * chains RAW stride-2 convolutions without waiting for any statistics: z[0] receives level 0's output, z[d]
+ * (d >= 1) the raw chain R_d [samples,C,L>>d]; a second small kernel reproduces every level's GlobLN from row
+ * statistics and leaves the coefficients of the merge in `scratch` (sdr_pyramid_scratch_bytes; 0 = shape not
+ * eligible: D < 4, L % 16, L >> (D-1) < 6, or rows too long for shared memory -> use sdr_depthwise / sdr_merge).
+ * w5[d] [C][5], bias[d] [C]: level d's depthwise conv; gamma[d] / beta[d] [C]: spp_dw[d].norm.
+ * stats0: zeroed (sum, sumsq) slot per sample for level 0's output.
+ * sdr_merge_pyramid then writes m[c,t] = sum_d GLN_d(z_d)[c, t>>d] (+ its statistics), reading z and scratch. */
+size_t sdr_pyramid_scratch_bytes(int samples, int C, int D, int L);
+int sdr_depthwise_pyramid(const float* y, const sdr_norm_in* fin, const float* const* w5, const float* const* bias,
+                          const float* const* gamma, const float* const* beta, float* const* z, double* stats0,
+                          void* scratch, int D, int samples, int C, int L, sdr_stream stream);
+int sdr_merge_pyramid(const float* const* z, const void* scratch, int D, float* m, double* stats_out,
+                      int samples, int C, int L, sdr_stream stream);
 
 /* nearest x2 up-sampling + skip adds, closed form
  * m[c,t] = sum_d norm_d(z_d)[c, t>>d] (improved_sudormrf.py:214-216).        */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "sdr_forward": (C.c_int, [C.POINTER(SdrConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                               C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sdr_forward_launch_count": (C.c_int, [C.POINTER(SdrConfig)]),
+    "sdr_forward_launch_count_at": (C.c_int, [C.POINTER(SdrConfig), C.c_int64]),
     "sdr_host_staging_bytes": (C.c_size_t, [C.POINTER(SdrConfig), C.c_int, C.c_int64]),
     "sdr_forward_host": (C.c_int, [C.POINTER(SdrConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
@@ -77,6 +78,12 @@ _SIGNATURES = {
     "sdr_depthwise": (C.c_int, [C.c_void_p, C.POINTER(SdrNormIn), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
+    "sdr_pyramid_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "sdr_depthwise_pyramid": (C.c_int, [C.c_void_p, C.POINTER(SdrNormIn), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sdr_merge_pyramid": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sdr_merge": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(SdrNormIn), C.c_int, C.c_void_p,
                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sdr_tac": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int,

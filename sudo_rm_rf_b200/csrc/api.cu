@@ -13,6 +13,13 @@ namespace sdr {
 // kernel launchers (levels.cu, pointwise.cu, frontback.cu, tac.cu)
 int launch_depthwise(const float*, const NormIn&, const float*, const float*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_merge(const float* const*, const NormIn*, int, float*, double*, int, int, int, cudaStream_t);
+// depthwise pyramid in one pass (pyramid.cu)
+bool pyramid_eligible(int D, int C, int L);
+size_t pyramid_rowstats_bytes(int samples, int C, int D);
+size_t pyramid_table_bytes(int samples, int C, int D);
+int launch_pyramid(const float*, const NormIn&, const float* const*, const float* const*, const float* const*,
+                   const float* const*, float* const*, double*, double*, float*, int, int, int, int, cudaStream_t);
+int launch_merge_pyramid(const float* const*, const float*, int, float*, double*, int, int, int, cudaStream_t);
 int launch_pointwise_ffma(const float*, const NormIn&, const float*, const float*, const float*, const float*, int,
                           float*, double*, int, int, int, int, int, cudaStream_t);
 int launch_encoder(const float*, const float*, float*, double*, int, int, long long, int, int, int, cudaStream_t);
@@ -169,6 +176,8 @@ struct Plan {
     long long Tp; int L; int samples;          // samples = B (improved) or B*G
     int slots; size_t stats_doubles;
     size_t o_stats, o_e, o_x, o_xt, o_o, o_y, o_z[kMaxDepthApi], o_masked, o_frames, total;  // bytes
+    bool pyramid;                              // the depthwise pyramid runs as one pass (pyramid.cu)
+    size_t o_rowstats, o_table;
 };
 
 static Plan make_plan(const Layout& l, int B, long long T) {
@@ -188,6 +197,9 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     p.o_o = l.gc ? seg(BL * l.Co) : 0;
     p.o_y = seg(BL * l.Ci);
     for (int d = 0; d < kMaxDepthApi; ++d) p.o_z[d] = d < l.D ? seg((BL * l.Ci) >> d) : 0;
+    p.pyramid = pyramid_eligible(l.D, l.cib, p.L);
+    p.o_rowstats = p.pyramid ? seg(pyramid_rowstats_bytes(p.samples, l.cib, l.D)) : 0;
+    p.o_table = p.pyramid ? seg(pyramid_table_bytes(p.samples, l.cib, l.D)) : 0;
     p.o_masked = seg(BL * l.S * l.A * l.N);
     p.o_frames = seg(BL * l.S * l.A * l.K);
     p.total = cur;
@@ -254,25 +266,48 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
         if (!proj_done)
             SDR_TRY(pointwise(bin, none, pk + u.proj_w, u.proj_pk ? pk + u.proj_pk : nullptr, pk + u.proj_b,
                               nullptr, nullptr, 0, y, slot(s0), ns, cib, cob, L, 0, st));
-        // level 0: PReLU(GLN(proj)) on load
-        {
+        bool pyr_done = false;
+        if (p.pyramid) {
+            // every depthwise level from ONE pass over y (raw convolution chain + row statistics), the GlobLN
+            // of every level solved afterwards, the merge as an affine combination of the raw tensors
             NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)cib * L};
-            SDR_TRY(launch_depthwise(y, n0, pk + u.dw_w[0], pk + u.dw_b[0], z[0], slot(s0 + 1), ns, cib, L, 1, st));
-        }
-        for (int d = 1; d < D; ++d) {
-            NormIn nd{slot(s0 + d), pk + u.dw_g[d - 1], pk + u.dw_be[d - 1], nullptr, (double)cib * (L >> (d - 1))};
-            SDR_TRY(launch_depthwise(z[d - 1], nd, pk + u.dw_w[d], pk + u.dw_b[d], z[d], slot(s0 + 1 + d),
-                                     ns, cib, L >> (d - 1), 2, st));
-        }
-        // merge
-        {
-            NormIn nm[kMaxDepthApi];
+            const float *pw[kMaxDepthApi], *pb[kMaxDepthApi], *pg[kMaxDepthApi], *pbe[kMaxDepthApi];
             const float* zc[kMaxDepthApi];
             for (int d = 0; d < D; ++d) {
-                nm[d] = NormIn{slot(s0 + 1 + d), pk + u.dw_g[d], pk + u.dw_be[d], nullptr, (double)cib * (L >> d)};
+                pw[d] = pk + u.dw_w[d]; pb[d] = pk + u.dw_b[d]; pg[d] = pk + u.dw_g[d]; pbe[d] = pk + u.dw_be[d];
                 zc[d] = z[d];
             }
-            SDR_TRY(launch_merge(zc, nm, D, y, slot(s0 + D + 1), ns, cib, L, st));   // m reuses y's storage
+            int rc = launch_pyramid(y, n0, pw, pb, pg, pbe, z, slot(s0 + 1), reinterpret_cast<double*>(ws + p.o_rowstats),
+                                    reinterpret_cast<float*>(ws + p.o_table), D, ns, cib, L, st);
+            if (rc == SDR_OK) {
+                SDR_TRY(launch_merge_pyramid(zc, reinterpret_cast<const float*>(ws + p.o_table), D, y, slot(s0 + D + 1),
+                                             ns, cib, L, st));                      // m reuses y's storage
+                pyr_done = true;
+            } else if (rc != SDR_ERR_UNSUPPORTED) {
+                return rc;
+            }
+        }
+        if (!pyr_done) {
+        // level 0: PReLU(GLN(proj)) on load
+            {
+                NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)cib * L};
+                SDR_TRY(launch_depthwise(y, n0, pk + u.dw_w[0], pk + u.dw_b[0], z[0], slot(s0 + 1), ns, cib, L, 1, st));
+            }
+            for (int d = 1; d < D; ++d) {
+                NormIn nd{slot(s0 + d), pk + u.dw_g[d - 1], pk + u.dw_be[d - 1], nullptr, (double)cib * (L >> (d - 1))};
+                SDR_TRY(launch_depthwise(z[d - 1], nd, pk + u.dw_w[d], pk + u.dw_b[d], z[d], slot(s0 + 1 + d),
+                                         ns, cib, L >> (d - 1), 2, st));
+            }
+            // merge
+            {
+                NormIn nm[kMaxDepthApi];
+                const float* zc[kMaxDepthApi];
+                for (int d = 0; d < D; ++d) {
+                    nm[d] = NormIn{slot(s0 + 1 + d), pk + u.dw_g[d], pk + u.dw_be[d], nullptr, (double)cib * (L >> d)};
+                    zc[d] = z[d];
+                }
+                SDR_TRY(launch_merge(zc, nm, D, y, slot(s0 + D + 1), ns, cib, L, st));   // m reuses y's storage
+            }
         }
         // res_conv + skip
         {
@@ -404,13 +439,25 @@ int sdr_forward(const sdr_config* cfg, const void* packed, const float* mixture,
                         static_cast<cudaStream_t>(stream));
 }
 
-int sdr_forward_launch_count(const sdr_config* cfg) {
+static int launch_count(const Layout& l, long long T) {
+    // encoder + bottleneck + U * (proj + levels + merge + res [+ tac (+ tac_apply unless it is folded into proj)])
+    // + mask + decoder GEMM + overlap-add; levels = pyramid + solve when the one-pass path takes the shape, else D launches
+    const bool folded = l.gc && l.U > 0 && !l.ub[0].proj_pk && l.cob <= 64 && l.cib <= 64 && l.D >= 2;   // L % 4 == 0 then
+    const int L = (int)(padded_len(l, T) / l.hop);
+    const int levels = pyramid_eligible(l.D, l.cib, L) ? 2 : l.D;
+    return 2 + l.U * (levels + 3 + (l.gc ? (folded ? 1 : 2) : 0)) + 3;
+}
+
+int sdr_forward_launch_count(const sdr_config* cfg) {          // at the reference's 4 s @ 8 kHz length
     const Layout l = make_layout(cfg);
     if (!l.ok) return SDR_ERR_BAD_CONFIG;
-    // encoder + bottleneck + U * (proj + D depthwise + merge + res [+ tac (+ tac_apply unless it is folded into proj)])
-    // + mask + decoder GEMM + overlap-add
-    const bool folded = l.gc && l.U > 0 && !l.ub[0].proj_pk && l.cob <= 64 && l.cib <= 64 && l.D >= 2;   // L % 4 == 0 then
-    return 2 + l.U * (l.D + 3 + (l.gc ? (folded ? 1 : 2) : 0)) + 3;
+    return launch_count(l, 32000);
+}
+
+int sdr_forward_launch_count_at(const sdr_config* cfg, int64_t T) {
+    const Layout l = make_layout(cfg);
+    if (!l.ok || T <= 0) return SDR_ERR_BAD_CONFIG;
+    return launch_count(l, T);
 }
 
 size_t sdr_host_staging_bytes(const sdr_config* cfg, int B, int64_t T) {
@@ -495,6 +542,35 @@ int sdr_depthwise(const float* x, const sdr_norm_in* fin, const float* w5, const
     if (stride == 2 && (Lin % 2)) return SDR_ERR_BAD_ARGUMENT;
     return launch_depthwise(x, make_norm(fin), w5, bias, y, stats_out, samples, C, Lin, stride,
                             static_cast<cudaStream_t>(stream));
+}
+
+static size_t pyr_table_offset(int samples, int C, int D) {
+    return (pyramid_rowstats_bytes(samples, C, D) + 255) & ~(size_t)255;
+}
+
+size_t sdr_pyramid_scratch_bytes(int samples, int C, int D, int L) {
+    if (samples <= 0 || !pyramid_eligible(D, C, L)) return 0;
+    return pyr_table_offset(samples, C, D) + pyramid_table_bytes(samples, C, D);
+}
+
+int sdr_depthwise_pyramid(const float* y, const sdr_norm_in* fin, const float* const* w5, const float* const* bias,
+                          const float* const* gamma, const float* const* beta, float* const* z, double* stats0,
+                          void* scratch, int D, int samples, int C, int L, sdr_stream stream) {
+    if (!y || !w5 || !bias || !gamma || !beta || !z || !stats0 || !scratch) return SDR_ERR_BAD_ARGUMENT;
+    if (!pyramid_eligible(D, C, L)) return SDR_ERR_UNSUPPORTED;
+    char* sc = static_cast<char*>(scratch);
+    return launch_pyramid(y, make_norm(fin), w5, bias, gamma, beta, z, stats0, reinterpret_cast<double*>(sc),
+                          reinterpret_cast<float*>(sc + pyr_table_offset(samples, C, D)), D, samples, C, L,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int sdr_merge_pyramid(const float* const* z, const void* scratch, int D, float* m, double* stats_out,
+                      int samples, int C, int L, sdr_stream stream) {
+    if (!z || !scratch || !m || !stats_out) return SDR_ERR_BAD_ARGUMENT;
+    if (!pyramid_eligible(D, C, L)) return SDR_ERR_UNSUPPORTED;
+    const char* sc = static_cast<const char*>(scratch);
+    return launch_merge_pyramid(z, reinterpret_cast<const float*>(sc + pyr_table_offset(samples, C, D)), D, m, stats_out,
+                                samples, C, L, static_cast<cudaStream_t>(stream));
 }
 
 int sdr_merge(const float* const* z, const sdr_norm_in* fins, int depth, float* m, double* stats_out,

@@ -80,6 +80,60 @@ def test_depthwise(samples, C_, L, stride, prelu):
     check_stats(stats_out, want)
 
 
+@pytest.mark.parametrize("samples,C_,L,D,prelu", [
+    (3, 512, 3200, 5, True),     # cfg 2 block
+    (2, 512, 3200, 6, True),     # cfg 3 block (last level: 100 positions)
+    (1, 512, 6400, 6, True),     # cfg 5 block
+    (5, 32, 3200, 5, True),      # GroupComm rows
+    (3, 7, 48, 4, True),         # shortest eligible rows: L >> (D-1) == 6, every run of the merge is an edge run
+    (2, 5, 96, 5, False), (2, 3, 192, 6, True), (4, 9, 112, 4, True), (2, 6, 1024, 6, True), (300, 4, 448, 4, True),
+])
+def test_depthwise_pyramid(samples, C_, L, D, prelu):
+    """sdr_depthwise_pyramid + sdr_merge_pyramid == the level-by-level chain in torch (improved_sudormrf.py:205-216)."""
+    lib = N.lib()
+    g = torch.Generator().manual_seed(11)
+    y = (torch.randn(samples, C_, L, generator=g) * 1.3 + 0.3).to(DEV)
+    gy = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
+    by = (0.2 * torch.randn(C_, generator=g)).to(DEV)
+    slope = torch.tensor([0.3], device=DEV) if prelu else None
+    ws = [torch.randn(C_, 1, 5, generator=g).to(DEV) * 0.6 for _ in range(D)]
+    bs = [torch.randn(C_, generator=g).to(DEV) * 0.5 for _ in range(D)]
+    gs = [(1 + 0.3 * torch.randn(C_, generator=g)).to(DEV) for _ in range(D)]
+    bes = [(0.2 * torch.randn(C_, generator=g)).to(DEV) for _ in range(D)]
+    nbytes = lib.sdr_pyramid_scratch_bytes(samples, C_, D, L)
+    assert nbytes > 0
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    zs = [torch.full((samples, C_, L >> d), float("nan"), device=DEV) for d in range(D)]
+    st0 = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    stm = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    m = torch.full((samples, C_, L), float("nan"), device=DEV)
+    arr = lambda ts: (C.c_void_p * D)(*[t.data_ptr() for t in ts])
+    nin = norm_in(raw_stats(y).to(DEV), gy, by, slope, C_ * L)
+    N.check(lib.sdr_depthwise_pyramid(p(y), C.byref(nin), arr(ws), arr(bs), arr(gs), arr(bes), arr(zs), p(st0),
+                                      p(scratch), D, samples, C_, L, stream()))
+    N.check(lib.sdr_merge_pyramid(arr(zs), p(scratch), D, p(m), p(stm), samples, C_, L, stream()))
+    # reference chain
+    cur = ref_norm(y, gy, by, slope)
+    levels = []
+    for d in range(D):
+        z = F.conv1d(cur, ws[d], bs[d], stride=1 if d == 0 else 2, padding=2, groups=C_)
+        if d == 0:
+            close(zs[0], z)
+            check_stats(st0, z)
+        cur = ref_norm(z, gs[d], bes[d])
+        levels.append(cur)
+    for _ in range(D - 1):
+        top = levels.pop()
+        levels[-1] = levels[-1] + F.interpolate(top, scale_factor=2, mode="nearest")
+    close(m, levels[0], tol=5e-5)            # the affine re-composition reorders fp32 roundings over D levels
+    check_stats(stm, levels[0], rtol=1e-4)
+    # not eligible: depth 3 or > 6, L not a multiple of 16, rows too short
+    assert lib.sdr_pyramid_scratch_bytes(samples, C_, 7, 1024) == 0
+    assert lib.sdr_pyramid_scratch_bytes(samples, C_, 3, L) == 0
+    assert lib.sdr_pyramid_scratch_bytes(samples, C_, D, L + 8) == 0
+    assert lib.sdr_pyramid_scratch_bytes(samples, C_, 6, 96) == 0
+
+
 @pytest.mark.parametrize("samples,C_,L,depth", [
     (2, 32, 3200, 5), (3, 16, 64, 6), (2, 8, 32, 1), (2, 5, 2, 1), (2, 6, 6, 2), (1, 512, 3200, 5),
     (2, 8, 48, 4), (2, 7, 128, 8), (3, 5, 24, 4), (2, 512, 6400, 6),
