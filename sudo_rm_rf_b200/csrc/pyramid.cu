@@ -45,7 +45,7 @@ struct PyrArgs {
     const float* bias0;             // bias of level 0: [C]
     float* z[kPyrMaxDepth];         // z[0] = z_0 (raw, with bias), z[d] = R_d (raw convolution chain)
     double* stats0;                 // per-sample (sum, sumsq) of z_0
-    double* rowstats;               // [rows][D - 1][kRowStat]
+    double* rowstats;               // [samples][D - 1][C][kRowStat]: a (sample, level) block is contiguous for the solve
     int D, C, L, rows;
 };
 
@@ -221,18 +221,32 @@ dw_pyramid_kernel(const PyrArgs a) {
         if (in_l) { const float2 h = *reinterpret_cast<const float2*>(yb + g0 - 2); u[0] = h.x; u[1] = h.y; }
         if (in_r) { const float2 h = *reinterpret_cast<const float2*>(yb + g0 + 16); u[18] = h.x; u[19] = h.y; }
     }
+    // (uniform branches: the slope's side of 1 and the row-edge lanes are decided once, not per element)
+    if (!act) {
 #pragma unroll
-    for (int i = 0; i < 20; ++i) {
-        float t = fmaf(u[i], na, nb);
-        if (act) { const float m = t * slope; t = sle1 ? fmaxf(t, m) : fminf(t, m); }
-        const bool in = i < 2 ? in_l : (i < 18 ? inrow : in_r);
-        u[i] = in ? t : 0.f;
+        for (int i = 0; i < 20; ++i) u[i] = fmaf(u[i], na, nb);
+    } else if (sle1) {
+#pragma unroll
+        for (int i = 0; i < 20; ++i) { const float t = fmaf(u[i], na, nb); u[i] = fmaxf(t, t * slope); }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 20; ++i) { const float t = fmaf(u[i], na, nb); u[i] = fminf(t, t * slope); }
+    }
+    if (!(inrow && in_l && in_r)) {                         // zero padding applies to u (not to y): exactly 0 outside the row
+        if (!in_l) { u[0] = 0.f; u[1] = 0.f; }
+        if (!in_r) { u[18] = 0.f; u[19] = 0.f; }
+        if (!inrow) {
+#pragma unroll
+            for (int i = 2; i < 18; ++i) u[i] = 0.f;
+        }
     }
 
     float part[2 * D];
 #pragma unroll
     for (int i = 0; i < 2 * D; ++i) part[i] = 0.f;
-    double* rs = a.rowstats + (size_t)row * (D - 1) * kRowStat;
+    const int c_row = row - sample * a.C;
+    double* rs = a.rowstats + ((size_t)sample * (D - 1) * a.C + c_row) * kRowStat;   // level 1; level d at + (d - 1) * rsl
+    const size_t rsl = (size_t)a.C * kRowStat;
 
     // ---- level 0 ----
     float z0[16];
@@ -245,7 +259,11 @@ dw_pyramid_kernel(const PyrArgs a) {
             acc = fmaf(w2_, u[i + 2], acc);
             acc = fmaf(w3_, u[i + 3], acc);
             acc = fmaf(w4_, u[i + 4], acc);
-            z0[i] = inrow ? acc : 0.f;                      // zero padding of level 1's input
+            z0[i] = acc;
+        }
+        if (!inrow) {                                       // zero padding of level 1's input
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z0[i] = 0.f;
         }
         if (valid) {
             float* zr = a.z[0] + (size_t)row * L + g0;
@@ -274,7 +292,11 @@ dw_pyramid_kernel(const PyrArgs a) {
             acc = fmaf(w2_, v[2 * i + 2], acc);
             acc = fmaf(w3_, v[2 * i + 3], acc);
             acc = fmaf(w4_, v[2 * i + 4], acc);
-            cur[i] = inrow ? acc : 0.f;
+            cur[i] = acc;
+        }
+        if (!inrow) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) cur[i] = 0.f;
         }
         if (valid) {
             const int Ld = L >> d;
@@ -291,12 +313,12 @@ dw_pyramid_kernel(const PyrArgs a) {
 #pragma unroll
             for (int i = 0; i < N; ++i) { part[2 * d] += cur[i]; part[2 * d + 1] = fmaf(cur[i], cur[i], part[2 * d + 1]); }
             if constexpr (N >= 2) {
-                if (g0 == 0) { rs[(d - 1) * kRowStat + 2] = (double)cur[0]; rs[(d - 1) * kRowStat + 3] = (double)cur[1]; }
+                if (g0 == 0) { rs[(d - 1) * rsl + 2] = (double)cur[0]; rs[(d - 1) * rsl + 3] = (double)cur[1]; }
             } else {
-                if (g0 == 0) rs[(d - 1) * kRowStat + 2] = (double)cur[0];
-                if (g0 == 16) rs[(d - 1) * kRowStat + 3] = (double)cur[0];
+                if (g0 == 0) rs[(d - 1) * rsl + 2] = (double)cur[0];
+                if (g0 == 16) rs[(d - 1) * rsl + 3] = (double)cur[0];
             }
-            if (g0 + 16 == L) rs[(d - 1) * kRowStat + 4] = (double)cur[N - 1];
+            if (g0 + 16 == L) rs[(d - 1) * rsl + 4] = (double)cur[N - 1];
         }
     };
     float r1[8], r2[4], r3[2], r4[1];
@@ -318,9 +340,9 @@ dw_pyramid_kernel(const PyrArgs a) {
             a.z[5][(size_t)row * (L >> 5) + (g0 >> 5)] = acc;
             part[10] += acc;
             part[11] = fmaf(acc, acc, part[11]);
-            if (g0 == 0) rs[4 * kRowStat + 2] = (double)acc;
-            if (g0 == 32) rs[4 * kRowStat + 3] = (double)acc;
-            if (g0 + 32 == L) rs[4 * kRowStat + 4] = (double)acc;
+            if (g0 == 0) rs[4 * rsl + 2] = (double)acc;
+            if (g0 == 32) rs[4 * rsl + 3] = (double)acc;
+            if (g0 + 32 == L) rs[4 * rsl + 4] = (double)acc;
         }
     }
 
@@ -337,7 +359,7 @@ dw_pyramid_kernel(const PyrArgs a) {
         double tot = 0.0;
         for (int wv = 0; wv < nw; ++wv) tot += (double)s_part[cur][wv][tid];
         if (tid < 2) atomicAdd(a.stats0 + 2 * (size_t)sample + tid, tot);
-        else rs[(tid / 2 - 1) * kRowStat + (tid & 1)] = tot;
+        else rs[(size_t)(tid / 2 - 1) * rsl + (tid & 1)] = tot;
     }
     }   // rows
 }
@@ -347,7 +369,7 @@ dw_pyramid_kernel(const PyrArgs a) {
 // ---------------------------------------------------------------------------
 struct SolveArgs {
     const double* stats0;           // per-sample (sum, sumsq) of z_0
-    const double* rowstats;         // [rows][D - 1][kRowStat]
+    const double* rowstats;         // [samples][D - 1][C][kRowStat]
     const float* gamma[kPyrMaxDepth];   // GlobLN of level d's OUTPUT (spp_dw[d].norm)
     const float* beta[kPyrMaxDepth];
     const float* w[kPyrMaxDepth];       // taps of level d
@@ -357,17 +379,19 @@ struct SolveArgs {
 };
 
 constexpr int kSolveThreads = 256;
+constexpr int kSolveKC = 2;                 // channels per thread: C <= 512 (wider layers take the per-level kernels)
 
+// Everything a level needs is loaded one level ahead into registers (row statistics of level d + 1, and the norm /
+// tap parameters used after level d's reduction), so a level costs its arithmetic and two barriers instead of three
+// dependent L2 round trips (22.7 us per launch in the first version, as much as 12 % of the pyramid itself).
 __global__ void __launch_bounds__(kSolveThreads)
 pyramid_solve_kernel(const SolveArgs a) {
-    extern __shared__ double sol_smem[];                  // per channel: alpha, k0, k1, kint, kr, Qacc
     __shared__ double s_red[2][kSolveThreads / 32];
     __shared__ double s_mean, s_rstd;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sample = blockIdx.x;
     const int D = a.D, C = a.C;
     const int TW = pyr_table_width(D);
-    double* st = sol_smem;                                // [C][6]
 
     auto block_norm = [&](double sz, double sq, double count) {   // all threads call; result in s_mean / s_rstd
 #pragma unroll
@@ -385,9 +409,41 @@ pyramid_solve_kernel(const SolveArgs a) {
         }
         __syncthreads();
     };
+    struct After { float g, be, w[5], bias; };              // used after level d's reduction: gamma_d, beta_d, taps / bias of level d + 1
+    auto load_after = [&](int d, int c) -> After {
+        After r;
+        r.g = __ldg(a.gamma[d] + c); r.be = __ldg(a.beta[d] + c);
+        if (d + 1 < D) {
+            const float* w = a.w[d + 1] + c * 5;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) r.w[j] = __ldg(w + j);
+            r.bias = __ldg(a.bias[d + 1] + c);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) r.w[j] = 0.f;
+            r.bias = 0.f;
+        }
+        return r;
+    };
+    struct Rs { double v[kRowStat]; };
+    auto load_rs = [&](int d, int c) -> Rs {                  // row statistics of level d (d >= 1)
+        Rs r;
+        const double* p = a.rowstats + (((size_t)sample * (D - 1) + (d - 1)) * C + c) * kRowStat;
+#pragma unroll
+        for (int k = 0; k < kRowStat; ++k) r.v[k] = p[k];
+        return r;
+    };
 
-    // level 0: statistics measured directly
-    if (tid == 0) {
+    // per-channel state: alpha, k0, k1, kint, kr of the level about to be reduced, and the Q accumulator
+    double al[kSolveKC], k0[kSolveKC], k1[kSolveKC], ki[kSolveKC], kr[kSolveKC], qa[kSolveKC];
+    Rs rs[kSolveKC];
+    After af[kSolveKC];
+#pragma unroll
+    for (int k = 0; k < kSolveKC; ++k) {
+        const int c = tid + k * kSolveThreads;
+        if (c < C) { af[k] = load_after(0, c); rs[k] = load_rs(1, c); }
+    }
+    if (tid == 0) {                                         // level 0: statistics measured directly
         const double cnt = (double)C * a.L;
         const double mu = a.stats0[2 * (size_t)sample] / cnt;
         double var = a.stats0[2 * (size_t)sample + 1] / cnt - mu * mu;
@@ -396,69 +452,79 @@ pyramid_solve_kernel(const SolveArgs a) {
         s_rstd = 1.0 / sqrt(var + (double)kGlnEps);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += kSolveThreads) {
-        const double A0 = (double)__ldg(a.gamma[0] + c) * s_rstd;
-        const double B0 = (double)__ldg(a.beta[0] + c) - s_mean * A0;
-        float* tb = a.table + ((size_t)sample * C + c) * TW;
-        tb[pyr_p_index(D, 0)] = (float)A0;
-        double* s = st + (size_t)c * 6;
-        // z_1 = alpha R_1 + kappa_1(t):  alpha = A0, kappa = B0 * (sum of in-bounds taps of level 1) + bias_1
-        const float* w = a.w[1] + c * 5;
-        const double w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
-        const double b1 = __ldg(a.bias[1] + c);
-        s[0] = A0;
-        s[1] = B0 * (w2 + w3 + w4) + b1;                  // t = 0: taps 0, 1 fall on the padding
-        s[3] = B0 * (w0 + w1 + w2 + w3 + w4) + b1;        // interior
-        s[2] = s[3];                                      // t = 1 is interior at level 1
-        s[4] = B0 * (w0 + w1 + w2 + w3) + b1;             // t = L_1 - 1: tap 4 falls on the padding
-        s[5] = B0;                                        // Q accumulator: sum_d (A_d kint_d + B_d), kint_0 = 0
+#pragma unroll
+    for (int k = 0; k < kSolveKC; ++k) {
+        const int c = tid + k * kSolveThreads;
+        if (c < C) {
+            const double A0 = (double)af[k].g * s_rstd;
+            const double B0 = (double)af[k].be - s_mean * A0;
+            a.table[((size_t)sample * C + c) * TW + pyr_p_index(D, 0)] = (float)A0;
+            // z_1 = alpha R_1 + kappa_1(t):  alpha = A0, kappa = B0 * (sum of in-bounds taps of level 1) + bias_1
+            const double w0 = af[k].w[0], w1 = af[k].w[1], w2 = af[k].w[2], w3 = af[k].w[3], w4 = af[k].w[4];
+            const double b1 = af[k].bias;
+            al[k] = A0;
+            k0[k] = B0 * (w2 + w3 + w4) + b1;               // t = 0: taps 0, 1 fall on the padding
+            ki[k] = B0 * (w0 + w1 + w2 + w3 + w4) + b1;     // interior
+            k1[k] = ki[k];                                  // t = 1 is interior at level 1
+            kr[k] = B0 * (w0 + w1 + w2 + w3) + b1;          // t = L_1 - 1: tap 4 falls on the padding
+            qa[k] = B0;                                     // sum_d (A_d kint_d + B_d), kint_0 = 0
+        }
     }
-    __syncthreads();
 
     for (int d = 1; d < D; ++d) {
         const int Ld = a.L >> d;
         double sz = 0.0, sq = 0.0;
-        for (int c = tid; c < C; c += kSolveThreads) {
-            const double* s = st + (size_t)c * 6;
-            const double* rs = a.rowstats + (((size_t)sample * C + c) * (D - 1) + (d - 1)) * kRowStat;
-            const double al = s[0], k0 = s[1], k1 = s[2], ki = s[3], kr = s[4];
-            const double sR = rs[0], sR2 = rs[1], R0 = rs[2], R1 = rs[3], Rl = rs[4];
-            sz += al * sR + (double)(Ld - 3) * ki + k0 + k1 + kr;
-            sq += al * al * sR2 + 2.0 * al * (ki * sR + (k0 - ki) * R0 + (k1 - ki) * R1 + (kr - ki) * Rl)
-                  + (double)(Ld - 3) * ki * ki + k0 * k0 + k1 * k1 + kr * kr;
-        }
-        block_norm(sz, sq, (double)C * Ld);
-        for (int c = tid; c < C; c += kSolveThreads) {
-            double* s = st + (size_t)c * 6;
-            const double Ad = (double)__ldg(a.gamma[d] + c) * s_rstd;
-            const double Bd = (double)__ldg(a.beta[d] + c) - s_mean * Ad;
-            const double al = s[0], k0 = s[1], k1 = s[2], ki = s[3], kr = s[4];
-            float* tb = a.table + ((size_t)sample * C + c) * TW;
-            tb[pyr_p_index(D, d)] = (float)(Ad * al);
-            tb[pyr_dq_index(D, d) + 0] = (float)(Ad * (k0 - ki));
-            tb[pyr_dq_index(D, d) + 1] = (float)(Ad * (k1 - ki));
-            tb[pyr_dq_index(D, d) + 2] = (float)(Ad * (kr - ki));
-            s[5] += Ad * ki + Bd;
-            if (d + 1 < D) {                               // z_{d+1} = (Ad alpha) R_{d+1} + Ad conv(kappa_d) + Bd S(t) + bias
-                const float* w = a.w[d + 1] + c * 5;
-                const double w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
-                const double bn = __ldg(a.bias[d + 1] + c);
-                const double S = w0 + w1 + w2 + w3 + w4;
-                const double c0 = w2 * k0 + w3 * k1 + w4 * ki;              // window -2 .. 2
-                const double c1 = w0 * k0 + w1 * k1 + (w2 + w3 + w4) * ki;  // window 0 .. 4
-                const double ci = S * ki;
-                const double cr = (w0 + w1 + w2) * ki + w3 * kr;            // window L_d - 4 .. L_d
-                s[0] = Ad * al;
-                s[1] = Ad * c0 + Bd * (w2 + w3 + w4) + bn;
-                s[2] = Ad * c1 + Bd * S + bn;
-                s[3] = Ad * ci + Bd * S + bn;
-                s[4] = Ad * cr + Bd * (w0 + w1 + w2 + w3) + bn;
+        Rs rn[kSolveKC];
+#pragma unroll
+        for (int k = 0; k < kSolveKC; ++k) {
+            const int c = tid + k * kSolveThreads;
+            if (c < C) {
+                af[k] = load_after(d, c);                   // consumed after the reduction below
+                if (d + 1 < D) rn[k] = load_rs(d + 1, c);   // consumed in the next iteration
+                const double sR = rs[k].v[0], sR2 = rs[k].v[1], R0 = rs[k].v[2], R1 = rs[k].v[3], Rl = rs[k].v[4];
+                sz += al[k] * sR + (double)(Ld - 3) * ki[k] + k0[k] + k1[k] + kr[k];
+                sq += al[k] * al[k] * sR2
+                      + 2.0 * al[k] * (ki[k] * sR + (k0[k] - ki[k]) * R0 + (k1[k] - ki[k]) * R1 + (kr[k] - ki[k]) * Rl)
+                      + (double)(Ld - 3) * ki[k] * ki[k] + k0[k] * k0[k] + k1[k] * k1[k] + kr[k] * kr[k];
             }
         }
-        __syncthreads();
+        block_norm(sz, sq, (double)C * Ld);
+#pragma unroll
+        for (int k = 0; k < kSolveKC; ++k) {
+            const int c = tid + k * kSolveThreads;
+            if (c < C) {
+                const double Ad = (double)af[k].g * s_rstd;
+                const double Bd = (double)af[k].be - s_mean * Ad;
+                float* tb = a.table + ((size_t)sample * C + c) * TW;
+                tb[pyr_p_index(D, d)] = (float)(Ad * al[k]);
+                tb[pyr_dq_index(D, d) + 0] = (float)(Ad * (k0[k] - ki[k]));
+                tb[pyr_dq_index(D, d) + 1] = (float)(Ad * (k1[k] - ki[k]));
+                tb[pyr_dq_index(D, d) + 2] = (float)(Ad * (kr[k] - ki[k]));
+                qa[k] += Ad * ki[k] + Bd;
+                if (d + 1 < D) {                            // z_{d+1} = (Ad alpha) R_{d+1} + Ad conv(kappa_d) + Bd S(t) + bias
+                    const double w0 = af[k].w[0], w1 = af[k].w[1], w2 = af[k].w[2], w3 = af[k].w[3], w4 = af[k].w[4];
+                    const double bn = af[k].bias;
+                    const double S = w0 + w1 + w2 + w3 + w4;
+                    const double c0 = w2 * k0[k] + w3 * k1[k] + w4 * ki[k];              // window -2 .. 2
+                    const double c1 = w0 * k0[k] + w1 * k1[k] + (w2 + w3 + w4) * ki[k];  // window 0 .. 4
+                    const double ci = S * ki[k];
+                    const double cr = (w0 + w1 + w2) * ki[k] + w3 * kr[k];               // window L_d - 4 .. L_d
+                    al[k] = Ad * al[k];
+                    k0[k] = Ad * c0 + Bd * (w2 + w3 + w4) + bn;
+                    k1[k] = Ad * c1 + Bd * S + bn;
+                    ki[k] = Ad * ci + Bd * S + bn;
+                    kr[k] = Ad * cr + Bd * (w0 + w1 + w2 + w3) + bn;
+                    rs[k] = rn[k];
+                }
+            }
+        }
+        // (block_norm's first barrier of the next level orders the reads of s_mean / s_rstd above before they are rewritten)
     }
-    for (int c = tid; c < C; c += kSolveThreads)
-        a.table[((size_t)sample * C + c) * TW + pyr_q_index()] = (float)st[(size_t)c * 6 + 5];
+#pragma unroll
+    for (int k = 0; k < kSolveKC; ++k) {
+        const int c = tid + k * kSolveThreads;
+        if (c < C) a.table[((size_t)sample * C + c) * TW + pyr_q_index()] = (float)qa[k];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -472,23 +538,6 @@ struct MergePyrArgs {
 };
 constexpr int kMpThreads = 128;
 constexpr int kMpItems = 2;
-
-// Edge corrections of one run of 16 outputs (3 of the 200 runs of a row at the benchmark shape); out of line so that
-// the common path keeps the register footprint of the plain merge.
-__device__ __noinline__ void merge_edge_fix(float (&o)[16], const float* tb, int D, int L, int q) {
-#pragma unroll 1
-    for (int d = 1; d < D; ++d) {
-        const float dq0 = __ldg(tb + pyr_dq_index(D, d)), dq1 = __ldg(tb + pyr_dq_index(D, d) + 1);
-        const float dqr = __ldg(tb + pyr_dq_index(D, d) + 2);
-        const int last = (L >> d) - 1;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int idx = (16 * q + i) >> d;
-            o[i] += idx == 0 ? dq0 : (idx == 1 ? dq1 : 0.f);
-            o[i] += idx == last ? dqr : 0.f;
-        }
-    }
-}
 
 __global__ void __launch_bounds__(kMpThreads)
 merge_pyramid_kernel(const MergePyrArgs a, float* __restrict__ m, double* __restrict__ stats_out, int chunks_per_sample) {
@@ -520,9 +569,6 @@ merge_pyramid_kernel(const MergePyrArgs a, float* __restrict__ m, double* __rest
             float base = qq.x;                                 // Q_int + the levels that are constant over the run
             if (D > 4) base = fmaf(__ldg(a.z[4] + row * (L >> 4) + q), qq.y, base);
             if (D > 5) base = fmaf(__ldg(a.z[5] + row * (L >> 5) + (q >> 1)), qq.z, base);
-            if (D > 6) base = fmaf(__ldg(a.z[6] + row * (L >> 6) + (q >> 2)), qq.w, base);
-            for (int d = 7; d < D; ++d)
-                base = fmaf(__ldg(a.z[d] + row * (L >> d) + (q >> (d - 4))), __ldg(tb + pyr_p_index(D, d)), base);
             const float p0 = pp.x, p1 = pp.y, p2 = pp.z, p3 = pp.w;
             float s3[2], s2[4], s1[8], o[16];
             s3[0] = fmaf(v3.x, p3, base); s3[1] = fmaf(v3.y, p3, base);
@@ -536,8 +582,21 @@ merge_pyramid_kernel(const MergePyrArgs a, float* __restrict__ m, double* __rest
                                    v02.x, v02.y, v02.z, v02.w, v03.x, v03.y, v03.z, v03.w};
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = fmaf(z0v[i], p0, s1[i >> 1]);
-            if (q < left_runs || q >= QR - right_runs)     // rows' ends: the padding of a level reaches these positions
-                merge_edge_fix(o, tb, D, L, q);
+            if (q < left_runs || q >= QR - right_runs) {   // rows' ends: the padding of a level reaches these positions
+                // (kept inline: as a __noinline__ helper taking o[] by reference the run lived in local memory: 120 -> 165 us)
+#pragma unroll 1
+                for (int d = 1; d < D; ++d) {
+                    const float dq0 = __ldg(tb + pyr_dq_index(D, d)), dq1 = __ldg(tb + pyr_dq_index(D, d) + 1);
+                    const float dqr = __ldg(tb + pyr_dq_index(D, d) + 2);
+                    const int last = (L >> d) - 1;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int idx = (16 * q + i) >> d;
+                        o[i] += idx == 0 ? dq0 : (idx == 1 ? dq1 : 0.f);
+                        o[i] += idx == last ? dqr : 0.f;
+                    }
+                }
+            }
             float* mr = m + row * L + 16 * q;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -558,7 +617,7 @@ static int pyramid_windows(int D, int L) {                     // warps per row
     return (L + step - 1) / step;
 }
 bool pyramid_eligible(int D, int C, int L) {
-    if (D < 4 || D > 6 || C <= 0) return false;                // levels 0..3 by lane chunks, 4 per lane, 5 per lane pair
+    if (D < 4 || D > 6 || C <= 0 || C > kSolveKC * kSolveThreads) return false;   // levels 0..3 by lane chunks, 4 per lane, 5 per lane pair
     if (L % 16 != 0 || (L % (1 << (D - 1))) != 0) return false;
     if ((L >> (D - 1)) < 6) return false;                      // the edge bookkeeping assumes 2 + 1 distinct edge positions
     return pyramid_windows(D, L) <= 32;                        // one CTA (<= 1024 threads) per row
@@ -611,11 +670,7 @@ int launch_pyramid(const float* y, const NormIn& nin, const float* const* w5, co
     };
     int rc = D == 4 ? launch(dw_pyramid_kernel<4>) : (D == 5 ? launch(dw_pyramid_kernel<5>) : launch(dw_pyramid_kernel<6>));
     if (rc != SDR_OK) return rc;
-    const size_t ssm = (size_t)C * 6 * sizeof(double);
-    if (ssm > 48 * 1024 &&
-        cudaFuncSetAttribute(pyramid_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm) != cudaSuccess)
-        return SDR_ERR_CUDA;
-    pyramid_solve_kernel<<<(unsigned)samples, kSolveThreads, ssm, st>>>(s);
+    pyramid_solve_kernel<<<(unsigned)samples, kSolveThreads, 0, st>>>(s);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
