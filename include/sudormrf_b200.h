@@ -245,6 +245,12 @@ int sdr_separate_ragged(const sdr_config* cfg, const void* packed, const float* 
  * SI-SNR (minus the batch-mean SI-SNR of the mixture when improvement != 0),
  * perm_index[b] = index of that permutation in itertools.permutations(range(S))
  * order.  1 <= S <= 4.  eps as in the reference's forward (default 1e-9).     */
+/* Pairwise negative SNR / SI-SDR / SD-SDR of a batch (dnn/losses/sisdr.py:372-457, PairwiseNegSDR.forward):
+ * out[b, i, j] = -sdr(estimate i, target j), [B, S, S] fp32; sdr_type 0 = "snr", 1 = "sisdr", 2 = "sdsdr".
+ * One fp64 Gram pass + a finalize kernel; scratch: sdr_pit_sisdr_scratch_bytes(B, S).  1 <= S <= 4.        */
+int sdr_pairwise_neg_sdr(const float* est, const float* target, float* out, int B, int S, int64_t T, int sdr_type,
+                         int zero_mean, int take_log, void* scratch, sdr_stream stream);
+
 size_t sdr_pit_sisdr_scratch_bytes(int B, int S);
 int sdr_pit_sisdr(const float* est, const float* target, const float* mixture_or_null,
                   float* best, int32_t* perm_index, int B, int S, int64_t T,

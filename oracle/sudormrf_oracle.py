@@ -402,6 +402,39 @@ def pit_sisdr(pr: Tensor, tgt: Tensor, mix: Optional[Tensor] = None, zero_mean: 
     return best, idx
 
 
+def pairwise_neg_sdr(est: Tensor, tgt: Tensor, sdr_type: str = "sisdr", zero_mean: bool = True,
+                     take_log: bool = True) -> Tensor:
+    """PairwiseNegSDR.forward (sisdr.py:416-457): [B, S, S], entry [b, i, j] = -sdr(estimate i, target j)."""
+    assert sdr_type in ("snr", "sisdr", "sdsdr")
+    if zero_mean:                                                         # sisdr.py:419-423
+        tgt = tgt - tgt.mean(dim=2, keepdim=True)
+        est = est - est.mean(dim=2, keepdim=True)
+    s_t = tgt.unsqueeze(1)                                                # sisdr.py:425-426
+    s_e = est.unsqueeze(2)
+    if sdr_type in ("sisdr", "sdsdr"):                                    # sisdr.py:428-435
+        dot = torch.sum(s_e * s_t, dim=3, keepdim=True)
+        energy = torch.sum(s_t ** 2, dim=3, keepdim=True) + 1e-8
+        proj = dot * s_t / energy
+    else:
+        proj = s_t.repeat(1, s_t.shape[2], 1, 1)                          # sisdr.py:438
+    noise = s_e - s_t if sdr_type in ("sdsdr", "snr") else s_e - proj     # sisdr.py:439-442
+    sdr = torch.sum(proj ** 2, dim=3) / (torch.sum(noise ** 2, dim=3) + 1e-8)   # sisdr.py:444-445
+    if take_log:
+        sdr = 10 * torch.log10(sdr + 1e-8)                                # sisdr.py:446-447
+    return -sdr
+
+
+def pit_from_pairwise(pw: Tensor):
+    """PITLossWrapper.find_best_perm with perm_reduce=None (sisdr.py:326-369): (min loss [B, 1], permutation index [B])."""
+    import itertools
+    n_src = pw.shape[1]
+    pwl = pw.transpose(-1, -2)
+    perms = list(itertools.permutations(range(n_src)))
+    loss_set = torch.stack([sum(pwl[:, j, p[j]] for j in range(n_src)) / n_src for p in perms], dim=1)
+    idx = torch.argmin(loss_set, dim=1)
+    return loss_set.min(dim=1, keepdim=True)[0], idx
+
+
 # --------------------------------------------------------------------------
 # tolerance used by every parity test (SURVEY §8d)
 # --------------------------------------------------------------------------

@@ -33,6 +33,7 @@ int launch_pointwise_small_preadd(const float*, const float*, const NormIn&, flo
 int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
 int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
 size_t pit_sisdr_scratch_bytes(int B, int S);
+int launch_pairwise_neg_sdr(const float*, const float*, float*, int, int, long long, int, int, int, void*, cudaStream_t);
 int launch_pit_sisdr(const float*, const float*, const float*, float*, int*, int, int, long long, int, int, double,
                      void*, cudaStream_t);
 // tensor-core path (pointwise_mma.cu)
@@ -658,6 +659,12 @@ int sdr_separate_ragged(const sdr_config* cfg, const void* packed, const float* 
     if (T <= 0 || padded_len(l, T) != T) return SDR_ERR_BAD_ARGUMENT;   // the bucket width is a padded length
     return separate_impl(cfg, packed, wav, lengths, out, B, T, apply_mixture_consistency, rescale,
                          workspace, workspace_bytes, stream);
+}
+
+int sdr_pairwise_neg_sdr(const float* est, const float* target, float* out, int B, int S, int64_t T, int sdr_type,
+                         int zero_mean, int take_log, void* scratch, sdr_stream stream) {
+    return launch_pairwise_neg_sdr(est, target, out, B, S, T, sdr_type, zero_mean, take_log, scratch,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 size_t sdr_pit_sisdr_scratch_bytes(int B, int S) { return pit_sisdr_scratch_bytes(B, S); }

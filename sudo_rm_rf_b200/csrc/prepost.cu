@@ -268,6 +268,73 @@ static int launch_pit_s(const float* est, const float* tgt, const float* mix, fl
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------
+// pairwise negative SNR / SI-SDR / SD-SDR (sisdr.py:372-457, PairwiseNegSDR): out[b, i, j] = -sdr(estimate i, target j),
+// from the same one-pass fp64 Gram as the PIT metric.  With d = <e_i, t_j>, tt = <t_j, t_j>, ee = <e_i, e_i>
+// (means removed when zero_mean) and c = d / (tt + 1e-8):
+//     sisdr:  |proj|^2 = c^2 tt,  |noise|^2 = ee - 2 c d + c^2 tt
+//     sdsdr:  |proj|^2 = c^2 tt,  |noise|^2 = ee - 2 d + tt
+//     snr:    |proj|^2 = tt,      |noise|^2 = ee - 2 d + tt
+//     sdr = |proj|^2 / (|noise|^2 + 1e-8);  take_log: 10 log10(sdr + 1e-8)
+// ---------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256)
+pairwise_finalize_kernel(const double* __restrict__ acc, float* __restrict__ out, int B, long long T,
+                         int sdr_type, int zero_mean, int take_log) {
+    using P = PitLayout<S>;
+    const double n = (double)T;
+    for (int b = blockIdx.x * 256 + threadIdx.x; b < B; b += gridDim.x * 256) {
+        const double* a = acc + (size_t)b * P::N;
+        double me[S], mt[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) { me[i] = zero_mean ? a[i] / n : 0.0; mt[i] = zero_mean ? a[S + i] / n : 0.0; }
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            const double ee = a[P::EE + i] - n * me[i] * me[i];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const double tt = a[P::TT + j] - n * mt[j] * mt[j];
+                const double d = a[P::ET + i * S + j] - n * me[i] * mt[j];
+                const double c = d / (tt + 1e-8);
+                const double proj = sdr_type == 0 ? tt : c * c * tt;                       // 0 snr, 1 sisdr, 2 sdsdr
+                double noise = sdr_type == 1 ? ee - 2.0 * c * d + c * c * tt : ee - 2.0 * d + tt;
+                if (noise < 0.0) noise = 0.0;
+                double v = proj / (noise + 1e-8);
+                if (take_log) v = 10.0 * log10(v + 1e-8);
+                out[((size_t)b * S + i) * S + j] = (float)(-v);
+            }
+        }
+    }
+}
+
+template <int S>
+static int launch_pairwise_s(const float* est, const float* tgt, float* out, int B, long long T, int sdr_type,
+                             int zero_mean, int take_log, double* acc, cudaStream_t st) {
+    using P = PitLayout<S>;
+    if (cudaMemsetAsync(acc, 0, sizeof(double) * P::N * B, st) != cudaSuccess) return SDR_ERR_CUDA;
+    int chunks = (int)((T + 4095) / 4096);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    const long long grid = (long long)B * chunks;
+    if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    pit_gram_kernel<S><<<(unsigned)grid, 256, 0, st>>>(est, tgt, nullptr, acc, T, chunks);
+    pairwise_finalize_kernel<S><<<(unsigned)((B + 255) / 256), 256, 0, st>>>(acc, out, B, T, sdr_type, zero_mean, take_log);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+int launch_pairwise_neg_sdr(const float* est, const float* tgt, float* out, int B, int S, long long T, int sdr_type,
+                            int zero_mean, int take_log, void* scratch, cudaStream_t st) {
+    if (!est || !tgt || !out || !scratch || B <= 0 || T <= 0 || sdr_type < 0 || sdr_type > 2) return SDR_ERR_BAD_ARGUMENT;
+    double* acc = static_cast<double*>(scratch);
+    switch (S) {
+        case 1: return launch_pairwise_s<1>(est, tgt, out, B, T, sdr_type, zero_mean, take_log, acc, st);
+        case 2: return launch_pairwise_s<2>(est, tgt, out, B, T, sdr_type, zero_mean, take_log, acc, st);
+        case 3: return launch_pairwise_s<3>(est, tgt, out, B, T, sdr_type, zero_mean, take_log, acc, st);
+        case 4: return launch_pairwise_s<4>(est, tgt, out, B, T, sdr_type, zero_mean, take_log, acc, st);
+        default: return SDR_ERR_UNSUPPORTED;
+    }
+}
+
 size_t pit_sisdr_scratch_bytes(int B, int S) {
     if (B <= 0 || S < 1 || S > 4) return 0;
     const int V = 2 * S + 1;

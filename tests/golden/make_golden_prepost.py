@@ -107,6 +107,35 @@ def make_sisdr():
     print(f"sisdr -> {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def make_pairwise():
+    """``prepost_pairwise.npz``: ``PairwiseNegSDR`` (dnn/losses/sisdr.py:372-457) for every sdr_type / zero_mean /
+    take_log combination and ``PITLossWrapper(..., pit_from='pw_mtx')`` (sisdr.py:197-369) on top of it."""
+    arrays = {}
+    g = torch.Generator().manual_seed(11)
+    ci = 0
+    for si, (S, T, B) in enumerate(((2, 4001, 3), (3, 1777, 2), (1, 900, 2), (4, 640, 2))):
+        tgt = torch.randn(B, S, T, generator=g) + 0.3
+        est = tgt[:, torch.randperm(S, generator=g)] * 0.7 + 0.4 * torch.randn(B, S, T, generator=g) + 0.1
+        arrays[f"s{si}/est"] = est.numpy()
+        arrays[f"s{si}/tgt"] = tgt.numpy()
+        for sdr_type in ("snr", "sisdr", "sdsdr"):
+            for zero_mean, take_log in ((True, True), (False, True), (True, False)):
+                fn = ref_sisdr.PairwiseNegSDR(sdr_type, zero_mean=zero_mean, take_log=take_log)
+                pw = fn(est, tgt)
+                loss = ref_sisdr.PITLossWrapper(fn, pit_from="pw_mtx")(est, tgt)
+                key = f"c{ci}"
+                arrays[key + "/meta"] = np.frombuffer(json.dumps(dict(S=S, T=T, B=B, signals=si, sdr_type=sdr_type,
+                                                                       zero_mean=zero_mean, take_log=take_log)).encode(),
+                                                      dtype=np.uint8)
+                arrays[key + "/pw"] = pw.numpy()
+                arrays[key + "/pit_loss"] = loss.numpy()
+                ci += 1
+    path = os.path.join(HERE, "prepost_pairwise.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"pairwise: {ci} cases -> {os.path.getsize(path)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     make_separate()
     make_sisdr()
+    make_pairwise()

@@ -12,7 +12,7 @@ import sudo_rm_rf_b200 as P
 from sudo_rm_rf_b200 import _native as N
 from sudo_rm_rf_b200 import sisdr as S
 from oracle import sudormrf_oracle as O
-from test_prepost_oracle import SEPARATE, load_separate, load_sisdr
+from test_prepost_oracle import GOLDEN_DIR, SEPARATE, load_separate, load_sisdr
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -207,3 +207,62 @@ def test_separate_corpus_equals_one_at_a_time(variant, kw, mc):
             xn = ((x - x.mean()) / (x.std() + 1e-9))[None, None]
             want = m.separate(xn, mixture_consistency=mc)[0]
             assert max(O.parity_errors(y[None], want[None])) < 1e-4
+
+
+def _pairwise_cases():
+    import json
+    import os
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN_DIR, "prepost_pairwise.npz"))
+    out, ci = [], 0
+    while f"c{ci}/meta" in z.files:
+        meta = json.loads(bytes(z[f"c{ci}/meta"]).decode())
+        si = meta["signals"]
+        out.append((meta, torch.from_numpy(z[f"s{si}/est"]), torch.from_numpy(z[f"s{si}/tgt"]),
+                    torch.from_numpy(z[f"c{ci}/pw"]), torch.from_numpy(z[f"c{ci}/pit_loss"])))
+        ci += 1
+    return out
+
+
+def test_pairwise_neg_sdr_and_pit_wrapper_golden():
+    """`sisdr.PairwiseNegSDR` / `PITLossWrapper` (same constructors as dnn/losses/sisdr.py:197-457) against the
+    reference's own outputs: 36 cases (snr / sisdr / sdsdr x zero_mean x take_log, 1-4 sources)."""
+    from sudo_rm_rf_b200 import sisdr as S
+    for meta, est, tgt, pw, loss in _pairwise_cases():
+        fn = S.PairwiseNegSDR(meta["sdr_type"], zero_mean=meta["zero_mean"], take_log=meta["take_log"])
+        with torch.no_grad():
+            got = fn(est.to(DEV), tgt.to(DEV))
+            got_loss = S.PITLossWrapper(fn, pit_from="pw_mtx")(est.to(DEV), tgt.to(DEV))
+        assert got.shape == pw.shape
+        if meta["take_log"]:
+            assert torch.allclose(got.cpu(), pw, atol=2e-3, rtol=0), (meta, (got.cpu() - pw).abs().max())     # dB
+        else:
+            assert torch.allclose(got.cpu(), pw, rtol=2e-4, atol=1e-6), meta
+        assert torch.allclose(got_loss.cpu(), loss, atol=2e-3, rtol=2e-4), meta
+
+
+def test_pit_wrapper_modes_and_reordering():
+    """pw_pt / perm_avg modes and return_est follow the asteroid semantics the reference file was copied from."""
+    from sudo_rm_rf_b200 import sisdr as S
+    g = torch.Generator().manual_seed(3)
+    tgt = torch.randn(5, 3, 2000, generator=g)
+    perm = [2, 0, 1]
+    est = (tgt[:, perm] + 0.05 * torch.randn(5, 3, 2000, generator=g)).to(DEV)
+    tgt = tgt.to(DEV)
+    pw = S.PairwiseNegSDR("sisdr")
+    with torch.no_grad():
+        loss, reordered = S.PITLossWrapper(pw, pit_from="pw_mtx")(est, tgt, return_est=True)
+        want = O.pairwise_neg_sdr(est.cpu(), tgt.cpu(), "sisdr")
+        assert torch.allclose(loss.cpu(), O.pit_from_pairwise(want)[0].mean(), atol=2e-3)
+        # the reordered estimates line up with the targets again
+        assert float((reordered - tgt).abs().mean()) < 0.1
+        single = lambda e, t: pw(e.unsqueeze(1), t.unsqueeze(1))[:, 0, 0]
+        loss_pt = S.PITLossWrapper(single, pit_from="pw_pt")(est, tgt)
+        assert torch.allclose(loss_pt, loss, atol=1e-3)
+        avg = lambda e, t: torch.stack([single(e[:, i], t[:, i]) for i in range(3)], 1).mean(1)
+        loss_avg = S.PITLossWrapper(avg, pit_from="perm_avg")(est, tgt)
+        assert torch.allclose(loss_avg, loss, atol=1e-3)
+    with pytest.raises(RuntimeError):
+        pw(est.cpu(), tgt.cpu())
+    with pytest.raises(ValueError):
+        S.PITLossWrapper(pw, pit_from="nope")

@@ -83,3 +83,28 @@ def test_pit_sisdr_live_against_reference():
     assert torch.allclose(best, want, atol=1e-5, rtol=0)
     allp = list(itertools.permutations(range(3)))
     assert [allp[int(i)] for i in idx] == [tuple(int(v) for v in r) for r in perms]
+
+
+def load_pairwise():
+    z = np.load(os.path.join(GOLDEN_DIR, "prepost_pairwise.npz"))
+    cases = []
+    ci = 0
+    while f"c{ci}/meta" in z.files:
+        meta = json.loads(bytes(z[f"c{ci}/meta"]).decode())
+        si = meta["signals"]
+        cases.append((meta, dict(est=torch.from_numpy(z[f"s{si}/est"]), tgt=torch.from_numpy(z[f"s{si}/tgt"]),
+                                 pw=torch.from_numpy(z[f"c{ci}/pw"]), pit_loss=torch.from_numpy(z[f"c{ci}/pit_loss"]))))
+        ci += 1
+    return cases
+
+
+def test_pairwise_neg_sdr_matches_reference_golden():
+    """The oracle restatement of PairwiseNegSDR / PITLossWrapper.find_best_perm against reference-generated goldens
+    (tests/golden/make_golden_prepost.py::make_pairwise): 4 signal sets x 3 sdr types x 3 flag combinations."""
+    cases = load_pairwise()
+    assert len(cases) == 36
+    for meta, t in cases:
+        pw = O.pairwise_neg_sdr(t["est"], t["tgt"], meta["sdr_type"], meta["zero_mean"], meta["take_log"])
+        assert torch.equal(pw, t["pw"]), meta               # same torch op sequence: bit-exact
+        loss, _ = O.pit_from_pairwise(pw)
+        assert torch.allclose(loss.mean(), t["pit_loss"], rtol=1e-6, atol=1e-6), meta
