@@ -55,6 +55,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Dense bf16 TFLOP/s (cuBLAS, burst) measured on this pool's B200s; fallback: the profiling guide's figure."""
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        if "bf16_tflops" in p:
+            return float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json, burst)"
+    return 1670.0, "fallback (B200_PROFILING.md)"
+
+
 # --------------------------------------------------------------------------
 # algorithmic bytes / flops model (SURVEY.md §8d), fp32, every intermediate
 # written once and read once
@@ -523,11 +533,18 @@ def time_block(w, B, stream, flush, dev, reps=7):
         whole()
     stream.synchronize()
     kernels = []
+    tpeak, tpeak_src = load_tensor_peak()
     for name, fn, nbytes, flops in launchers:
         t = med(fn)
-        kernels.append({"kernel": name, "avg_launch_ms": t, "algorithmic_bytes_per_launch": nbytes,
-                        "achieved": nbytes / t / 1e6, "frac": nbytes / t / 1e6 / peak,
-                        "tflops_fp32_equivalent": flops / t / 1e9})
+        k = {"kernel": name, "avg_launch_ms": t, "algorithmic_bytes_per_launch": nbytes,
+             "achieved": nbytes / t / 1e6, "frac": nbytes / t / 1e6 / peak,
+             "tflops_fp32_equivalent": flops / t / 1e9}
+        if "tcgen05" in name:       # fp32-grade result from 3 bf16 products per MAC: the tensor pipe sees 3x the flops
+            k["bf16_tflops_issued"] = 3.0 * flops / t / 1e9
+            k["frac_tensor"] = 3.0 * flops / t / 1e9 / tpeak
+            k["tensor_peak_tflops"] = tpeak
+            k["tensor_peak_source"] = tpeak_src
+        kernels.append(k)
     t_blk = med(whole)
     gc = w["variant"] == "groupcomm"
     blk_bytes = B * (am["a_blk"] - (4 * am["L"] * 4 * w["kw"]["out_channels"] if gc else 0))   # TAC is not in this sequence

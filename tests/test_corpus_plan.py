@@ -42,3 +42,20 @@ def test_plan_splits_large_buckets_and_is_deterministic():
     assert plan_buckets([], 320, 8) == []
     with pytest.raises(ValueError):
         plan_buckets([10], 320, 0)
+
+
+def test_wav_roundtrip(tmp_path):
+    """load_wav follows torchaudio.load's conventions ([channels, T] float32 in [-1, 1], sample rate)."""
+    import numpy as np
+    import torch
+    from scipy.io import wavfile
+    from sudo_rm_rf_b200 import corpus as Cp
+    x = (torch.randn(2, 1234) * 0.3).clamp(-1, 1)
+    p = str(tmp_path / "f32.wav")
+    Cp.save_wav(p, x, 8000)
+    y, sr = Cp.load_wav(p)
+    assert sr == 8000 and torch.equal(x, y)
+    p16 = str(tmp_path / "i16.wav")
+    wavfile.write(p16, 16000, (x[0].numpy() * 32767).astype(np.int16))
+    y, sr = Cp.load_wav(p16)
+    assert sr == 16000 and y.shape == (1, 1234) and float((y[0] - x[0]).abs().max()) < 1e-4

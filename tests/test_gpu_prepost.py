@@ -266,3 +266,37 @@ def test_pit_wrapper_modes_and_reordering():
         pw(est.cpu(), tgt.cpu())
     with pytest.raises(ValueError):
         S.PITLossWrapper(pw, pit_from="nope")
+
+
+def test_corpus_separator_pipeline_equals_bucketed_loop(tmp_path):
+    """CorpusSeparator (pinned staging, copy streams, CUDA graph per bucket) == separate_corpus, bit for bit, on a second
+    and third pass too (graph capture, then replay); wav files in, wav files out (simple_whamr_evaluation.py:138-148)."""
+    from sudo_rm_rf_b200 import corpus as Cp
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+              enc_kernel_size=21, enc_num_basis=48, num_sources=2)
+    cfg = O.Config(variant="improved", **kw)
+    m = build("improved", kw, O.make_state_dict(cfg, seed=3))
+    g = torch.Generator().manual_seed(8)
+    lengths = [4000, 3999, 3850, 4160, 4001, 2000, 2100, 4000, 3900, 160, 90, 4100, 3841]
+    wavs = [torch.randn(n, generator=g) * (0.2 + 0.1 * i) + 0.05 * i for i, n in enumerate(lengths)]
+    want = Cp.separate_corpus(m, wavs, max_batch=4)
+    sep = Cp.CorpusSeparator(m, max_batch=4)
+    for _ in range(3):
+        got = sep.run(wavs)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert not a.is_cuda and torch.equal(a, b.cpu())
+    assert sep.launches["captured"] > 0 and sep.launches["replayed"] > 0
+    # wav files
+    paths = []
+    for i, w in enumerate(wavs[:5]):
+        p = str(tmp_path / f"mix{i}.wav")
+        Cp.save_wav(p, w, 8000)
+        paths.append(p)
+    written = Cp.separate_wav_files(m, paths, str(tmp_path / "out"), max_samples=4000, max_batch=4)
+    assert len(written) == 5 and all(len(w) == 2 for w in written)
+    ref = Cp.separate_corpus(m, [w[:4000] for w in wavs[:5]], max_batch=4)
+    for outs, r in zip(written, ref):
+        for k, path in enumerate(outs):
+            y, sr = Cp.load_wav(path)
+            assert sr == 8000 and torch.equal(y[0], r[k].cpu())
