@@ -130,8 +130,11 @@ __device__ __forceinline__ void pyr_bulk_g2s(void* dst, const void* src, uint32_
 // a double buffer and its per-row parameters by 4-byte cp.async while the current row is computed, so no thread ever
 // waits on a global load (one CTA per row with plain loads measured 1.7 us per row and SM: launch-to-first-use
 // latency of y, of the 28 parameters and of the fp64 statistics in every CTA).  One barrier per row.
-template <int D>
-__global__ void __launch_bounds__(1024)
+#ifndef SDR_PYR_MINB
+#define SDR_PYR_MINB 6                  // resident CTAs per SM the <= 256-thread instantiation is compiled for (A/B on the B200: 4 -> 177 us, 5 -> 175, 6 -> 165 at cfg 2)
+#endif
+template <int D, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 dw_pyramid_kernel(const PyrArgs a) {
     static_assert(D >= 4 && D <= 6, "register pyramid: levels 0..3 by lane chunks, 4 per lane, 5 per lane pair");
     constexpr int S = PyrGeom<D>::kStep, ML = PyrGeom<D>::kLeft;
@@ -668,7 +671,13 @@ int launch_pyramid(const float* y, const NormIn& nin, const float* const* w5, co
         kern<<<(unsigned)grid, threads, smem, st>>>(a);
         return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
     };
-    int rc = D == 4 ? launch(dw_pyramid_kernel<4>) : (D == 5 ? launch(dw_pyramid_kernel<5>) : launch(dw_pyramid_kernel<6>));
+    int rc;
+    if (threads <= 256)      // rows up to 7-8 windows (L <= 3712 / 3328): compiled for several resident CTAs per SM
+        rc = D == 4 ? launch(dw_pyramid_kernel<4, 256, SDR_PYR_MINB>)
+                    : (D == 5 ? launch(dw_pyramid_kernel<5, 256, SDR_PYR_MINB>) : launch(dw_pyramid_kernel<6, 256, SDR_PYR_MINB>));
+    else
+        rc = D == 4 ? launch(dw_pyramid_kernel<4, 1024, 1>)
+                    : (D == 5 ? launch(dw_pyramid_kernel<5, 1024, 1>) : launch(dw_pyramid_kernel<6, 1024, 1>));
     if (rc != SDR_OK) return rc;
     pyramid_solve_kernel<<<(unsigned)samples, kSolveThreads, 0, st>>>(s);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
