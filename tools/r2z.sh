@@ -15,6 +15,6 @@ print('eager', d['eager_cuda_baseline']['value'], 'cpu', d['cpu_baseline']['valu
 timeout -k 10 300 python bench.py --impl reference --steps 10 --warmup 1 2>/dev/null | tail -1 | cut -c1-200
 timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/r2z_launches.csv python tools/profile_forward.py --iters 2 > /dev/null 2>&1
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"pw_mma_kernel|dw_pyramid|merge_pyramid|pyramid_solve" -s 42 -c 5 \
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"pw_mma_kernel|dw_pyramid|merge_pyramid|pyramid_solve" -s 84 -c 7 \
     -o gpurun_out/prof_r2z_block -f python tools/profile_forward.py --iters 2 > gpurun_out/r2z_ncu.log 2>&1
 tail -1 gpurun_out/r2z_ncu.log
