@@ -42,7 +42,17 @@ WORKLOADS = {
     "improved_u36_4096_16k": dict(variant="improved", B=32, T=64000, kw=dict(
         out_channels=512, in_channels=512, num_blocks=36, upsampling_depth=6,
         enc_kernel_size=21, enc_num_basis=4096, num_sources=2)),
+    # SURVEY 8f.3 sibling variant (not a BASELINE config): CausalSuDORMRF with its constructor defaults
+    # (causal_improved_sudormrf_v3.py:121-129) at the headline batch / length
+    "causal_u16_512": dict(variant="causal", B=32, T=32000, kw=dict(
+        in_audio_channels=1, out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+        enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
 }
+
+
+def model_class(variant):
+    import sudo_rm_rf_b200 as P
+    return {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}[variant]
 METRIC = "mixtures_per_sec_forward_4s_8kHz_2src"
 UNIT = "mixtures/s"
 
@@ -79,6 +89,14 @@ def algorithmic_model(w):
     L = Tp // hop
     kappa = 5 + sum(2.0 ** -(d - 1) + 2.0 ** -d for d in range(1, D)) + sum(2.0 ** -d for d in range(D))
     a_blk = 4 * L * (3 * Co + kappa * Ci)
+    if w["variant"] == "causal":
+        # no normalisation layers: the depthwise stage is one local pass, so the model is the fused schedule's own
+        # minimum (x read, y written + read, m written + read, residual read, x written), not the level-by-level one
+        a_blk = 4 * L * (3 * Co + 4 * Ci)
+        a_mix = 4 * (Tp + 2 * N * L + Co * L) + U * a_blk + 4 * (Co * L + S * Tp)
+        flops = 2 * L * (K * N + N * Co + U * (2 * Co * Ci + 11 * Ci * (2 - 2.0 ** (1 - D))) + Co * S * N + K * S * S * N)
+        return dict(L=L, Tp=Tp, a_blk=a_blk, a_mix=a_mix, flops=flops,
+                    res_bytes=4 * L * (Ci + 2 * Co), res_flops=2 * Co * Ci * L)
     gc = w["variant"] == "groupcomm"
     if gc:
         a_blk += 4 * L * 4 * Co
@@ -242,8 +260,7 @@ def run_b200(args, w, wl_name):
         dist.init_process_group("nccl", device_id=dev)
 
     B, T = (args.batch or w["B"]), w["T"]
-    cls = P.SuDORMRF if w["variant"] == "improved" else P.GroupCommSudoRmRf
-    model = cls(**w["kw"])
+    model = model_class(w["variant"])(**w["kw"])
     cfg_o = O.Config(variant=w["variant"], **w["kw"])
     if rank == 0:
         model.load_state_dict(O.make_state_dict(cfg_o, seed=0, perturbed=False))
@@ -324,7 +341,7 @@ def run_b200(args, w, wl_name):
     if wl_name == "improved_u16_512" and not args.no_other_configs:
         del graph
         torch.cuda.empty_cache()
-        for name in ("improved_u36_2048", "groupcomm_u8_512", "improved_u36_4096_16k"):
+        for name in ("improved_u36_2048", "groupcomm_u8_512", "improved_u36_4096_16k", "causal_u16_512"):
             ow, ms, n_par = short_config_run(name, dev, stream, flush)
             others.append((name, ow, n_par))
             other_ms.append(ms)
@@ -360,6 +377,10 @@ def run_b200(args, w, wl_name):
                                   "samples": ow["T"], "steps": 5, "ms_per_step": ms,
                                   "value": ow["B"] * world / (ms / 1e3), "unit": UNIT,
                                   "forward_hbm_frac": ob / (ms / 1e3) / 1e9 / peak})
+            if ow["variant"] == "causal":      # the sibling variant's own kernels, each alone and as one block
+                ck, cpb, _, _ = time_block(ow, ow["B"], stream, flush, dev)
+                other_configs[-1]["kernels"] = ck
+                other_configs[-1]["per_block"] = cpb
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -396,6 +417,11 @@ def run_b200(args, w, wl_name):
 # --------------------------------------------------------------------------
 # per-kernel and per-U-ConvBlock timing through the stage-level C-ABI entry points
 # --------------------------------------------------------------------------
+def arrD_(ts, D):
+    import ctypes as C
+    return (C.c_void_p * D)(*[t.data_ptr() for t in ts])
+
+
 def block_launchers(w, B, dev, stream):
     """The 3 + D kernels of ONE U-ConvBlock at the workload's shapes, in forward order, as
     [(name, launch, algorithmic_bytes, flops)], operating on synthetic tensors through the stage-level C-ABI
@@ -444,9 +470,24 @@ def block_launchers(w, B, dev, stream):
                                                P(yout), P(stats), S, M, K, L, 0, sp))
         return name + " [pw_gemm_kernel FFMA]", fn
 
-    # proj_1x1: raw residual stream in, raw y + statistics out
     none = N.SdrNormIn(0, 0, 0, 0, 1.0)
     keep.append(none)
+    if w["variant"] == "causal":
+        # causal block (causal_improved_sudormrf_v3.py:98-118): proj GEMM, the whole depthwise stage in one pass,
+        # res_conv (gain folded into its weights) + in-place skip connection; no statistics anywhere
+        n_, f_ = gemm("proj_1x1", x, none, Ci, Co, None, y, None)
+        out.append((n_, f_, 4 * L * S * (Co + Ci), 2.0 * Co * Ci * L * S))
+        w21, b21 = [rn(Ci, 1, 21) * 0.3 for _ in range(D)], [rn(Ci) for _ in range(D)]
+        slopes = [slope] * D
+        wa, ba, sa = arrD_(w21, D), arrD_(b21, D), arrD_(slopes, D)
+        keep.extend([w21, b21, wa, ba, sa])
+        out.append((f"causal depthwise stage: PReLU, {D} masked 21-tap levels, up-sample + add, one pass [causal_pyramid_kernel]",
+                    lambda: N.check(lib.sdr_causal_pyramid(P(y), P(slope), wa, ba, sa, P(z[0]), D, S, Ci, L, sp)),
+                    4 * S * Ci * 2 * L, 22.0 * Ci * S * sum(L >> d for d in range(D))))
+        n_, f_ = gemm("res_conv+skip", z[0], none, Co, Ci, x, x, None)
+        out.append((n_, f_, 4 * L * S * (Ci + 2 * Co), 2.0 * Co * Ci * L * S))
+        return out, (lambda: None), keep
+    # proj_1x1: raw residual stream in, raw y + statistics out
     n_, f_ = gemm("proj_1x1", x, none, Ci, Co, None, y, st[0])
     out.append((n_, f_, 4 * L * S * (Co + Ci), 2.0 * Co * Ci * L * S))
     arrD = lambda ts: (C.c_void_p * D)(*[t.data_ptr() for t in ts])
@@ -551,8 +592,9 @@ def time_block(w, B, stream, flush, dev, reps=7):
     per_block = {"ms": t_blk, "sum_of_kernels_ms": sum(k["avg_launch_ms"] for k in kernels),
                  "algorithmic_bytes": blk_bytes, "achieved": blk_bytes / t_blk / 1e6, "peak": peak, "unit": "GB/s",
                  "frac": blk_bytes / t_blk / 1e6 / peak,
-                 "what": "proj_1x1 -> depthwise levels -> merge -> res_conv+skip of one U-ConvBlock at the benchmark shape, "
-                         "launched back to back through the stage-level C-ABI (L2 flushed before the block)"}
+                 "what": ("proj_1x1 -> causal depthwise stage -> res_conv+skip" if w["variant"] == "causal" else
+                          "proj_1x1 -> depthwise levels -> merge -> res_conv+skip") + " of one U-ConvBlock at the benchmark "
+                         "shape, launched back to back through the stage-level C-ABI (L2 flushed before the block)"}
     del keep
     return kernels, per_block, peak, peak_src
 
@@ -615,8 +657,7 @@ def short_config_run(name, dev, stream, flush, steps=5, warmup=3):
     import sudo_rm_rf_b200 as P
     from oracle import sudormrf_oracle as O
     w = WORKLOADS[name]
-    cls = P.SuDORMRF if w["variant"] == "improved" else P.GroupCommSudoRmRf
-    model = cls(**w["kw"])
+    model = model_class(w["variant"])(**w["kw"])
     model.load_state_dict(O.make_state_dict(O.Config(variant=w["variant"], **w["kw"]), seed=0, perturbed=False))
     model = model.to(dev).eval()
     x = torch.rand(w["B"], 1, w["T"], generator=torch.Generator().manual_seed(7)).to(dev)

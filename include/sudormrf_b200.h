@@ -37,11 +37,12 @@ extern "C" {
 #define SDR_ERR_CUDA          -4   /* a CUDA call or launch failed */
 #define SDR_ERR_UNSUPPORTED   -5   /* valid for the reference, not implemented here */
 
-/* Constructor arguments of the two reference models:
+/* Constructor arguments of the reference models:
  *   improved_sudormrf.py:224-231   SuDORMRF.__init__
- *   groupcomm_sudormrf_v2.py:232-241 GroupCommSudoRmRf.__init__            */
+ *   groupcomm_sudormrf_v2.py:232-241 GroupCommSudoRmRf.__init__
+ *   causal_improved_sudormrf_v3.py:121-129 CausalSuDORMRF.__init__         */
 typedef struct {
-    int32_t variant;            /* 0 = improved SuDORMRF, 1 = GroupCommSudoRmRf */
+    int32_t variant;            /* 0 = improved SuDORMRF, 1 = GroupCommSudoRmRf, 2 = CausalSuDORMRF */
     int32_t in_audio_channels;  /* 1 for improved */
     int32_t out_channels;
     int32_t in_channels;
@@ -60,7 +61,10 @@ const char* sdr_error_string(int code);
 
 /* Number of parameter tensors in the reference's state_dict() order
  * (improved_sudormrf.py:247-281, :170-196; groupcomm_sudormrf_v2.py:262-299,
- * :347-354, :401-403) and the element count of parameter i.                 */
+ * :347-354, :401-403; causal_improved_sudormrf_v3.py:146-189, :71-96) and the
+ * element count of parameter i.  For the causal model the caller passes
+ * skipinit_gain already multiplied by the block's alpha and proj_1x1's weight
+ * divided by its beta (both 1.0 in the reference's constructor, :165-174).    */
 int     sdr_num_params(const sdr_config* cfg);
 int64_t sdr_param_numel(const sdr_config* cfg, int index);
 
@@ -83,7 +87,8 @@ int    sdr_pack_weights(const sdr_config* cfg,
 size_t sdr_workspace_bytes(const sdr_config* cfg, int B, int64_t T);
 
 /* SuDORMRF.forward (improved_sudormrf.py:283-301) /
- * GroupCommSudoRmRf.forward (groupcomm_sudormrf_v2.py:302-322), optionally
+ * GroupCommSudoRmRf.forward (groupcomm_sudormrf_v2.py:302-322) /
+ * CausalSuDORMRF.forward (causal_improved_sudormrf_v3.py:191-211), optionally
  * followed by mixture_consistency.apply(..., 'uniform')
  * (mixture_consistency.py:14-36; only when in_audio_channels == 1).
  *   mixture: device [B, in_audio_channels, T] fp32 contiguous
@@ -188,6 +193,15 @@ int sdr_depthwise_pyramid(const float* y, const sdr_norm_in* fin, const float* c
                           void* scratch, int D, int samples, int C, int L, sdr_stream stream);
 int sdr_merge_pyramid(const float* const* z, const void* scratch, int D, float* m, double* stats_out,
                       int samples, int C, int L, sdr_stream stream);
+
+/* The depthwise stage of the causal U-ConvBlock (causal_improved_sudormrf_v3.py:106-116) in one pass: PReLU of
+ * proj_1x1 on load (slope_in), D levels of [causally masked 21-tap depthwise conv (stride 1, then 2) + bias + PReLU]
+ * kept in shared memory, nearest up-sampling and adds, m[c,t] = sum_d o_d[c, t>>d].  No normalisation layers exist
+ * in this block, so nothing crosses CTAs.  y, m [samples,C,L]; w21[d] [C][1][21] in the reference's layout (the 10
+ * taps the causal mask zeroes, :21-27, are not read); bias[d] [C]; slope_in, slope[d]: one float each.
+ * L % 4 == 0 and L % 2^D == 0 (every padded length is), else SDR_ERR_UNSUPPORTED.                              */
+int sdr_causal_pyramid(const float* y, const float* slope_in, const float* const* w21, const float* const* bias,
+                       const float* const* slope, float* m, int D, int samples, int C, int L, sdr_stream stream);
 
 /* nearest x2 up-sampling + skip adds, closed form
  * m[c,t] = sum_d norm_d(z_d)[c, t>>d] (improved_sudormrf.py:214-216).        */

@@ -11,6 +11,7 @@ reference tree (``/root/reference``):
 
   improved_sudormrf.py   = sudo_rm_rf/dnn/models/improved_sudormrf.py
   groupcomm_sudormrf_v2.py = sudo_rm_rf/dnn/models/groupcomm_sudormrf_v2.py
+  causal_improved_sudormrf_v3.py = sudo_rm_rf/dnn/models/causal_improved_sudormrf_v3.py
   mixture_consistency.py = sudo_rm_rf/dnn/experiments/utils/mixture_consistency.py
   README.md              = the reference's README (inference recipe, lines 100-114)
   sisdr.py               = sudo_rm_rf/dnn/losses/sisdr.py (validation metric)
@@ -42,12 +43,13 @@ Tensor = torch.Tensor
 # --------------------------------------------------------------------------
 @dataclass(frozen=True)
 class Config:
-    """Constructor arguments of the two reference models.
+    """Constructor arguments of the reference models.
 
-    improved_sudormrf.py:224-231 (SuDORMRF) and
-    groupcomm_sudormrf_v2.py:232-241 (GroupCommSudoRmRf).
+    improved_sudormrf.py:224-231 (SuDORMRF),
+    groupcomm_sudormrf_v2.py:232-241 (GroupCommSudoRmRf) and
+    causal_improved_sudormrf_v3.py:121-129 (CausalSuDORMRF).
     """
-    variant: str = "improved"          # "improved" | "groupcomm"
+    variant: str = "improved"          # "improved" | "groupcomm" | "causal"
     out_channels: int = 128
     in_channels: int = 512
     num_blocks: int = 16
@@ -55,7 +57,7 @@ class Config:
     enc_kernel_size: int = 21
     enc_num_basis: int = 512
     num_sources: int = 2
-    in_audio_channels: int = 1         # groupcomm only
+    in_audio_channels: int = 1         # groupcomm and causal only
     group_size: int = 16               # groupcomm only
 
     @property
@@ -109,6 +111,8 @@ def param_shapes(cfg: Config) -> Dict[str, tuple]:
     """Ordered name -> shape map, in the reference's ``state_dict()`` order."""
     N, Co, Ci = cfg.enc_num_basis, cfg.out_channels, cfg.in_channels
     S, D, k = cfg.num_sources, cfg.upsampling_depth, cfg.enc_kernel_size
+    if cfg.variant == "causal":
+        return _causal_param_shapes(cfg)
     A = cfg.in_audio_channels if cfg.variant == "groupcomm" else 1
     s: Dict[str, tuple] = {}
     s["encoder.weight"] = (N, A, k)                  # improved_sudormrf.py:247-251
@@ -141,6 +145,35 @@ def param_shapes(cfg: Config) -> Dict[str, tuple]:
     return s
 
 
+def _causal_param_shapes(cfg: Config) -> Dict[str, tuple]:
+    """causal_improved_sudormrf_v3.py:146-197 (model), :71-95 (block): no norms, a scalar ``skipinit_gain`` per
+    block, one PReLU slope per ConvAct, 21-tap depthwise filters, a (2k-1)-tap encoder, a PReLU on the masks."""
+    N, Co, Ci = cfg.enc_num_basis, cfg.out_channels, cfg.in_channels
+    S, D, k, A = cfg.num_sources, cfg.upsampling_depth, cfg.enc_kernel_size, cfg.in_audio_channels
+    s: Dict[str, tuple] = {}
+    s["encoder.weight"] = (N, A, 2 * k - 1)          # :146-151
+    s["bottleneck.weight"] = (Co, N, 1)              # :155-158
+    s["bottleneck.bias"] = (Co,)
+    for i in range(cfg.num_blocks):
+        p = f"sm.{i}."
+        s[p + "skipinit_gain"] = ()                  # :73
+        s[p + "proj_1x1.conv.weight"] = (Ci, Co, 1)
+        s[p + "proj_1x1.conv.bias"] = (Ci,)
+        s[p + "proj_1x1.act.weight"] = (1,)
+        for d in range(D):
+            s[p + f"spp_dw.{d}.conv.weight"] = (Ci, 1, 21)     # :78-90
+            s[p + f"spp_dw.{d}.conv.bias"] = (Ci,)
+            s[p + f"spp_dw.{d}.act.weight"] = (1,)
+        s[p + "res_conv.weight"] = (Co, Ci, 1)       # :96
+        s[p + "res_conv.bias"] = (Co,)
+    s["mask_net.0.weight"] = (1,)                    # :175-177
+    s["mask_net.1.weight"] = (S * N * A, Co, 1)
+    s["mask_net.1.bias"] = (S * N * A,)
+    s["decoder.weight"] = (N * S * A, S * A, k)      # :180-187
+    s["mask_nl_class.weight"] = (1,)                 # :189
+    return s
+
+
 def make_state_dict(cfg: Config, seed: int = 0, perturbed: bool = True,
                     dtype=torch.float32) -> Dict[str, Tensor]:
     """Seeded synthetic weights with the reference's names and shapes.
@@ -153,12 +186,16 @@ def make_state_dict(cfg: Config, seed: int = 0, perturbed: bool = True,
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {}
     for name, shape in param_shapes(cfg).items():
-        if not perturbed:
+        if name.endswith("skipinit_gain"):
+            # the reference initialises it to 0 (every block the identity); the synthetic weights use a gain that keeps
+            # the residual stream O(1) while making every block matter
+            t = 0.5 + 0.2 * torch.rand(shape, generator=g) if perturbed else torch.zeros(shape)
+        elif not perturbed:
             if name.endswith("gamma"):
                 t = torch.ones(shape)
             elif name.endswith("beta"):
                 t = torch.zeros(shape)
-            elif name.endswith("act.weight") or name in ("mask_net.0.weight",) or \
+            elif name.endswith("act.weight") or name in ("mask_net.0.weight", "mask_nl_class.weight") or \
                     (name.endswith(".1.weight") and "TAC" in name):
                 t = torch.full(shape, 0.25)
             else:
@@ -298,6 +335,8 @@ def forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor,
 
     wav: [B, A, T] (A = 1, or in_audio_channels for groupcomm) -> [B, S*A, T].
     """
+    if cfg.variant == "causal":
+        return causal_forward(cfg, sd, wav, taps=taps, dtype=dtype)
     if wav.dim() != 3:
         raise RuntimeError("expected a 3-D input [batch, audio_channels, time]")
     sd = {k: v.to(device=wav.device, dtype=dtype) for k, v in sd.items()}   # (bench.py times this op sequence on cuda too)
@@ -330,6 +369,71 @@ def forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor,
                            sd["decoder.weight"], None, stride=hop, padding=hop,
                            output_padding=hop - 1)                          # :300
     return y[..., :T]                                                       # :301
+
+
+def causal_weight(w: Tensor) -> Tensor:
+    """ScaledWSConv1d.get_weight, causal_improved_sudormrf_v3.py:21-27: the last ``kernel_size // 2`` taps (the
+    future samples under the symmetric padding) are zeroed; kernels shorter than 3 are left alone."""
+    ks = w.shape[-1]
+    if ks < 3:
+        return w
+    m = torch.ones_like(w)
+    m[..., -(ks // 2):] = 0.
+    return w * m
+
+
+def causal_uconv_block(x: Tensor, sd: Dict[str, Tensor], p: str, depth: int, alpha: float = 1.0, beta: float = 1.0,
+                       taps: Optional[dict] = None) -> Tensor:
+    """causal_improved_sudormrf_v3.py:98-118."""
+    Ci = sd[p + "proj_1x1.conv.weight"].shape[0]
+    residual = x
+    o = F.conv1d(x / beta, sd[p + "proj_1x1.conv.weight"], sd[p + "proj_1x1.conv.bias"])       # :105
+    if taps is not None:
+        taps[p + "proj_1x1.conv"] = o
+    o = prelu1(o, sd[p + "proj_1x1.act.weight"])
+    outs = []
+    for d in range(depth):                                                                      # :106-111
+        o = F.conv1d(o, causal_weight(sd[p + f"spp_dw.{d}.conv.weight"]), sd[p + f"spp_dw.{d}.conv.bias"],
+                     stride=1 if d == 0 else 2, padding=10, groups=Ci)
+        if taps is not None:
+            taps[p + f"spp_dw.{d}.conv"] = o
+        o = prelu1(o, sd[p + f"spp_dw.{d}.act.weight"])
+        outs.append(o)
+    for _ in range(depth - 1):                                                                  # :114-116
+        up = F.interpolate(outs.pop(-1), scale_factor=2, mode="nearest")
+        outs[-1] = outs[-1] + up
+    if taps is not None:
+        taps[p + "merged"] = outs[-1]
+    y = F.conv1d(outs[-1], sd[p + "res_conv.weight"], sd[p + "res_conv.bias"])
+    return y * sd[p + "skipinit_gain"] * alpha + residual                                       # :118
+
+
+def causal_forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor, taps: Optional[dict] = None,
+                   dtype=torch.float32) -> Tensor:
+    """CausalSuDORMRF.forward, causal_improved_sudormrf_v3.py:191-211.  wav [B, A, T] -> [B, S*A, T]."""
+    if wav.dim() != 3:
+        raise RuntimeError("expected a 3-D input [batch, audio_channels, time]")
+    sd = {k: v.to(device=wav.device, dtype=dtype) for k, v in sd.items()}
+    T = wav.shape[-1]
+    k, hop = cfg.enc_kernel_size, cfg.hop
+    x = pad_wave(cfg, wav, dtype)                                                               # :193
+    x = F.conv1d(x, causal_weight(sd["encoder.weight"]), None, stride=hop, padding=(2 * k - 1) // 2)   # :194
+    if taps is not None:
+        taps["encoder"] = x
+    x = F.conv1d(x, sd["bottleneck.weight"], sd["bottleneck.bias"])                             # :199
+    if taps is not None:
+        taps["bottleneck"] = x
+    for i in range(cfg.num_blocks):                                                             # :200
+        x = causal_uconv_block(x, sd, f"sm.{i}.", cfg.upsampling_depth, taps=taps)
+        if taps is not None:
+            taps[f"sm.{i}.out"] = x
+    x = prelu1(x, sd["mask_net.0.weight"])                                                      # :202
+    x = F.conv1d(x, sd["mask_net.1.weight"], sd["mask_net.1.bias"])
+    if taps is not None:
+        taps["mask_net.1"] = x
+    x = prelu1(x, sd["mask_nl_class.weight"])                                                   # :206 (no product with the encoder output, :207)
+    y = F.conv_transpose1d(x, sd["decoder.weight"], None, stride=hop, padding=hop, output_padding=hop - 1)   # :209
+    return y[..., :T]                                                                           # :210
 
 
 def mixture_consistency(est: Tensor, mix: Tensor,

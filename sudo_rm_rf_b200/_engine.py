@@ -23,13 +23,16 @@ _warned_detached = False
 def make_config(model) -> N.SdrConfig:
     """Constructor arguments -> ``sdr_config``; reads the public attributes the
     reference stores (improved_sudormrf.py:235-241, groupcomm_sudormrf_v2.py:245-252)."""
-    gc = hasattr(model, "in_audio_channels")
+    variant = getattr(model, "_b200_variant", None)
+    if variant is None:
+        variant = 1 if hasattr(model, "in_audio_channels") else 0
+    gc = variant == 1
     group = 1
     if gc:
         group = int(getattr(model, "group_size", 0) or
                     (model.sm[0].num_group if len(model.sm) else 16))
     return N.SdrConfig(
-        variant=1 if gc else 0,
+        variant=int(variant),
         in_audio_channels=int(getattr(model, "in_audio_channels", 1)),
         out_channels=int(model.out_channels), in_channels=int(model.in_channels),
         num_blocks=int(model.num_blocks), upsampling_depth=int(model.upsampling_depth),
@@ -40,6 +43,16 @@ def make_config(model) -> N.SdrConfig:
 def state_dict_names(cfg: N.SdrConfig) -> List[str]:
     """Parameter names in the reference's ``state_dict()`` order
     (improved_sudormrf.py:247-281,170-196; groupcomm_sudormrf_v2.py:347-354,401-403)."""
+    if cfg.variant == 2:       # causal_improved_sudormrf_v3.py:146-189, block :71-96
+        names = ["encoder.weight", "bottleneck.weight", "bottleneck.bias"]
+        for i in range(cfg.num_blocks):
+            p = f"sm.{i}."
+            names += [p + "skipinit_gain", p + "proj_1x1.conv.weight", p + "proj_1x1.conv.bias", p + "proj_1x1.act.weight"]
+            for d in range(cfg.upsampling_depth):
+                names += [p + f"spp_dw.{d}.conv.weight", p + f"spp_dw.{d}.conv.bias", p + f"spp_dw.{d}.act.weight"]
+            names += [p + "res_conv.weight", p + "res_conv.bias"]
+        names += ["mask_net.0.weight", "mask_net.1.weight", "mask_net.1.bias", "decoder.weight", "mask_nl_class.weight"]
+        return names
     names = ["encoder.weight", "ln.gamma", "ln.beta", "bottleneck.weight", "bottleneck.bias"]
 
     def ublock(p):
@@ -227,13 +240,17 @@ def packed_weights(model, cfg: N.SdrConfig, device) -> torch.Tensor:
     if n != len(tensors):
         raise N.NativeError(f"parameter inventory mismatch: library expects {n}, module has {len(tensors)}")
     flat = []
+    transform = getattr(model, "_b200_param_transform", None)     # constants the reference applies around a parameter
     for i, (name, t) in enumerate(zip(names, tensors)):
         if t.device != device:
             raise RuntimeError(f"parameter {name} is on {t.device}, input is on {device}")
         want = lib.sdr_param_numel(C.byref(cfg), i)
         if t.numel() != want:
             raise RuntimeError(f"parameter {name} has {t.numel()} elements, expected {want}")
-        flat.append(t.detach().to(torch.float32).contiguous())
+        t = t.detach().to(torch.float32)
+        if transform is not None:
+            t = transform(name, t)
+        flat.append(t.contiguous())
     nbytes = lib.sdr_packed_weight_bytes(C.byref(cfg))
     # the master (and a replica on the master's device, which shares this state) may have graphs / in-flight
     # kernels on the old buffer: always pack into a fresh one, the allocator recycles it stream-safely

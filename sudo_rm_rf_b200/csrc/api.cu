@@ -22,13 +22,19 @@ int launch_pyramid(const float*, const NormIn&, const float* const*, const float
 int launch_merge_pyramid(const float* const*, const float*, int, float*, double*, int, int, int, cudaStream_t);
 int launch_pointwise_ffma(const float*, const NormIn&, const float*, const float*, const float*, const float*, int,
                           float*, double*, int, int, int, int, int, cudaStream_t);
-int launch_encoder(const float*, const float*, float*, double*, int, int, long long, int, int, int, cudaStream_t);
+int launch_encoder(const float*, const float*, float*, double*, int, int, long long, int, int, int, int, cudaStream_t);
 int launch_overlap_add(const float*, const float*, const float2*, float*, int, int, int, int, long long, cudaStream_t);
 int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
 int launch_pointwise_small_preadd(const float*, const float*, const NormIn&, float*, const float*, const float*, float*,
                                   double*, int, int, int, int, cudaStream_t);
+// causal model (causal.cu)
+bool causal_pyramid_eligible(int D, int L);
+int launch_causal_pyramid(const float*, const float*, const float* const*, const float* const*, const float* const*, float*,
+                          int, int, int, int, cudaStream_t);
+int launch_take_taps(const float*, float*, long long, int, int, cudaStream_t);
+int launch_scale_by_scalar(const float*, const float*, float*, long long, cudaStream_t);
 // pre/post steps (prepost.cu)
 int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
 int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
@@ -45,7 +51,7 @@ int launch_pointwise_mma(const float*, const NormIn&, const void*, const float*,
 
 size_t encoder_mma_packed_bytes(int N, int A, int Kk);
 int pack_encoder_mma(const float* W, int N, int A, int Kk, void* packed, cudaStream_t);
-int launch_encoder_mma(const float*, const void*, float*, double*, int, int, long long, int, int, int, cudaStream_t);
+int launch_encoder_mma(const float*, const void*, float*, double*, int, int, long long, int, int, int, int, cudaStream_t);
 
 // One 1x1 convolution: tensor cores when the channel counts fill a tcgen05 tile, FFMA otherwise.
 static int pointwise(const float* x, const NormIn& nin, const float* W, const float* wpk, const float* bias,
@@ -68,12 +74,24 @@ struct UBlockOff {
     size_t proj_pk, res_pk;       // tensor-core images (0 = not eligible -> FFMA kernel)
 };
 struct TacOff { size_t p[9]; size_t g, be; };
+// causal_improved_sudormrf_v3.py:71-96: one scalar gain, proj (conv + PReLU), D x (21-tap depthwise + PReLU), res_conv
+struct CausalBlockOff {
+    size_t gain, proj_w, proj_b, proj_a;
+    size_t dw_w[kMaxDepthApi], dw_b[kMaxDepthApi], dw_a[kMaxDepthApi];
+    size_t res_w, res_b;
+    size_t res_wg, res_bg;        // derived: gain * res_conv.{weight,bias}
+    size_t proj_pk, res_pk;
+};
 
 struct Layout {
     bool ok = false;
     int A, N, Co, Ci, U, D, K, S, G, hop;
     int cob, cib;                 // channels seen by one U-ConvBlock (Co/G, Ci/G for groupcomm)
     bool gc;
+    bool causal = false;          // variant 2: CausalSuDORMRF
+    std::vector<CausalBlockOff> cb;
+    size_t mask_nl = 0;           // causal: mask_nl_class.weight (PReLU on the masks)
+    size_t enc_wc = 0;            // causal: derived [N][A][K], the encoder taps the causal mask keeps
     size_t enc_w, ln_g, ln_be, bn_w, bn_b, mask_a, mask_w, mask_b, dec_w;
     size_t dec_wt;                // derived: decoder weight as [S*A*K, S*A*N]
     size_t bn_pk, mask_pk, dec_pk, enc_pk; // derived: tensor-core weight images (0 = not eligible)
@@ -87,8 +105,9 @@ static Layout make_layout(const sdr_config* c) {
     Layout l;
     if (!c) return l;
     l.gc = c->variant == 1;
-    if (c->variant != 0 && c->variant != 1) return l;
-    l.A = l.gc ? c->in_audio_channels : 1;
+    l.causal = c->variant == 2;
+    if (c->variant < 0 || c->variant > 2) return l;
+    l.A = (l.gc || l.causal) ? c->in_audio_channels : 1;
     l.N = c->enc_num_basis; l.Co = c->out_channels; l.Ci = c->in_channels;
     l.U = c->num_blocks; l.D = c->upsampling_depth; l.K = c->enc_kernel_size;
     l.S = c->num_sources; l.G = l.gc ? c->group_size : 1;
@@ -102,6 +121,53 @@ static Layout make_layout(const sdr_config* c) {
 
     size_t cur = 0;
     auto add = [&](size_t n) { size_t o = cur; l.off.push_back(o); l.numel.push_back(n); cur += (n + 3) & ~(size_t)3; return o; };
+    if (l.causal) {
+        // state_dict order of CausalSuDORMRF (causal_improved_sudormrf_v3.py:146-189; block :71-96)
+        l.enc_w = add((size_t)l.N * l.A * (2 * l.K - 1));
+        l.ln_g = l.ln_be = 0;
+        l.bn_w = add((size_t)l.Co * l.N); l.bn_b = add(l.Co);
+        for (int i = 0; i < l.U; ++i) {
+            CausalBlockOff u;
+            u.gain = add(1);
+            u.proj_w = add((size_t)l.Ci * l.Co); u.proj_b = add(l.Ci); u.proj_a = add(1);
+            for (int d = 0; d < l.D; ++d) { u.dw_w[d] = add((size_t)l.Ci * 21); u.dw_b[d] = add(l.Ci); u.dw_a[d] = add(1); }
+            u.res_w = add((size_t)l.Co * l.Ci); u.res_b = add(l.Co);
+            l.cb.push_back(u);
+        }
+        l.mask_a = add(1);
+        l.mask_w = add((size_t)l.S * l.N * l.A * l.Co); l.mask_b = add((size_t)l.S * l.N * l.A);
+        l.dec_w = add((size_t)l.N * l.S * l.A * l.S * l.A * l.K);
+        l.mask_nl = add(1);
+        // derived regions
+        auto derived = [&](size_t n) { size_t o = cur; cur += (n + 3) & ~(size_t)3; return o; };
+        l.dec_wt = derived((size_t)l.S * l.A * l.K * l.S * l.A * l.N);
+        l.enc_wc = derived((size_t)l.N * l.A * l.K);
+        for (int i = 0; i < l.U; ++i) {
+            l.cb[i].res_wg = derived((size_t)l.Co * l.Ci);
+            l.cb[i].res_bg = derived(l.Co);
+        }
+        cur = (cur + 63) & ~(size_t)63;
+        auto add_pk = [&](int M, int K) -> size_t {
+            const size_t b = pointwise_mma_packed_bytes(M, K);
+            if (!b) return 0;
+            const size_t o = cur; cur += b / sizeof(float); return o;
+        };
+        l.bn_pk = add_pk(l.Co, l.N);
+        for (int i = 0; i < l.U; ++i) {
+            l.cb[i].proj_pk = add_pk(l.Ci, l.Co);
+            l.cb[i].res_pk = add_pk(l.Co, l.Ci);
+        }
+        l.mask_pk = add_pk(l.S * l.A * l.N, l.Co);
+        l.dec_pk = add_pk(l.S * l.A * l.K, l.S * l.A * l.N);
+        {
+            const size_t b = encoder_mma_packed_bytes(l.N, l.A, l.K);
+            l.enc_pk = b ? cur : 0;
+            cur += b / sizeof(float);
+        }
+        l.total = cur;
+        l.ok = true;
+        return l;
+    }
     l.enc_w = add((size_t)l.N * l.A * l.K);
     l.ln_g = add(l.N); l.ln_be = add(l.N);
     l.bn_w = add((size_t)l.Co * l.N); l.bn_b = add(l.Co);
@@ -186,7 +252,7 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     p.Tp = padded_len(l, T);
     p.L = (int)(p.Tp / l.hop);
     p.samples = B * l.G;
-    p.slots = 1 + l.U * (l.D + 2 + (l.gc ? 1 : 0));
+    p.slots = l.causal ? 1 : 1 + l.U * (l.D + 2 + (l.gc ? 1 : 0));
     p.stats_doubles = (size_t)p.slots * p.samples * 2;
     size_t cur = 0;
     auto seg = [&](size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~(size_t)255; return o; };
@@ -197,8 +263,8 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     p.o_xt = l.gc ? seg(BL * l.Co) : 0;
     p.o_o = l.gc ? seg(BL * l.Co) : 0;
     p.o_y = seg(BL * l.Ci);
-    for (int d = 0; d < kMaxDepthApi; ++d) p.o_z[d] = d < l.D ? seg((BL * l.Ci) >> d) : 0;
-    p.pyramid = pyramid_eligible(l.D, l.cib, p.L);
+    for (int d = 0; d < kMaxDepthApi; ++d) p.o_z[d] = (d < l.D && !(l.causal && d > 0)) ? seg((BL * l.Ci) >> d) : 0;
+    p.pyramid = !l.causal && pyramid_eligible(l.D, l.cib, p.L);
     p.o_rowstats = p.pyramid ? seg(pyramid_rowstats_bytes(p.samples, l.cib, l.D)) : 0;
     p.o_table = p.pyramid ? seg(pyramid_table_bytes(p.samples, l.cib, l.D)) : 0;
     p.o_masked = seg(BL * l.S * l.A * l.N);
@@ -208,12 +274,58 @@ static Plan make_plan(const Layout& l, int B, long long T) {
 }
 
 
+// CausalSuDORMRF.forward (causal_improved_sudormrf_v3.py:191-211): no normalisation anywhere, so nothing is deferred
+// except the PReLUs, which ride on the consumers' operand loads.
+static int forward_causal(const Layout& l, const float* pk, const float* mixture, float* out,
+                          int B, long long T, int apply_mc, char* ws, cudaStream_t st, const float2* rescale) {
+    const Plan p = make_plan(l, B, T);
+    const int L = p.L, D = l.D;
+    if (!causal_pyramid_eligible(D, L)) return SDR_ERR_UNSUPPORTED;
+    float* e = reinterpret_cast<float*>(ws + p.o_e);
+    float* x = reinterpret_cast<float*>(ws + p.o_x);
+    float* y = reinterpret_cast<float*>(ws + p.o_y);
+    float* m = reinterpret_cast<float*>(ws + p.o_z[0]);
+    float* masked = reinterpret_cast<float*>(ws + p.o_masked);
+    float* frames = reinterpret_cast<float*>(ws + p.o_frames);
+    const NormIn none{nullptr, nullptr, nullptr, nullptr, 1.0};
+    // encoder (:194): 2k-1 taps of which the causal mask keeps the first k, i.e. the improved model's encoder reading
+    // one hop further into the past (left padding 2 * hop)
+    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
+    else SDR_TRY(launch_encoder(mixture, pk + l.enc_wc, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
+    SDR_TRY(pointwise(e, none, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
+                      x, nullptr, B, l.Co, l.N, L, 0, st));                                      // :199
+    for (int i = 0; i < l.U; ++i) {
+        const CausalBlockOff& u = l.cb[i];
+        SDR_TRY(pointwise(x, none, pk + u.proj_w, u.proj_pk ? pk + u.proj_pk : nullptr, pk + u.proj_b, nullptr, nullptr, 0,
+                          y, nullptr, B, l.Ci, l.Co, L, 0, st));                                  // :105 (PReLU deferred)
+        const float *w[kMaxDepthApi], *b[kMaxDepthApi], *a[kMaxDepthApi];
+        for (int d = 0; d < D; ++d) { w[d] = pk + u.dw_w[d]; b[d] = pk + u.dw_b[d]; a[d] = pk + u.dw_a[d]; }
+        SDR_TRY(launch_causal_pyramid(y, pk + u.proj_a, w, b, a, m, D, B, l.Ci, L, st));          // :106-116
+        SDR_TRY(pointwise(m, none, pk + u.res_wg, u.res_pk ? pk + u.res_pk : nullptr, pk + u.res_bg, x, nullptr, 0,
+                          x, nullptr, B, l.Co, l.Ci, L, 0, st));                                  // :118
+    }
+    {
+        NormIn pm{nullptr, nullptr, nullptr, pk + l.mask_a, 1.0};                                 // :202 PReLU -> 1x1
+        SDR_TRY(pointwise(x, pm, pk + l.mask_w, l.mask_pk ? pk + l.mask_pk : nullptr, pk + l.mask_b, nullptr, nullptr, 0,
+                          masked, nullptr, B, l.S * l.A * l.N, l.Co, L, 0, st));
+    }
+    {
+        NormIn pn{nullptr, nullptr, nullptr, pk + l.mask_nl, 1.0};                                // :206 PReLU, :209 decoder
+        SDR_TRY(pointwise(masked, pn, pk + l.dec_wt, l.dec_pk ? pk + l.dec_pk : nullptr, nullptr, nullptr, nullptr, 0,
+                          frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
+    }
+    const float* mix = apply_mc ? mixture : nullptr;
+    SDR_TRY(launch_overlap_add(frames, mix, rescale, out, B, l.S * l.A, l.K, L, T, st));
+    return SDR_OK;
+}
+
 static int forward_impl(const Layout& l, const float* pk, const float* mixture, float* out,
                         int B, long long T, int apply_mc, char* ws, cudaStream_t st,
                         const float2* rescale = nullptr) {
     // mixture_consistency.apply (mixture_consistency.py:14-36) sums the estimates over dim 1 and broadcasts against a
     // [B, 1, T] mixture: it is only defined for mono models; refuse instead of silently skipping the projection
     if (apply_mc && l.A != 1) return SDR_ERR_UNSUPPORTED;
+    if (l.causal) return forward_causal(l, pk, mixture, out, B, T, apply_mc, ws, st, rescale);
     const Plan p = make_plan(l, B, T);
     const int L = p.L, D = l.D;
     double* stats = reinterpret_cast<double*>(ws + p.o_stats);
@@ -232,8 +344,8 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
 
     // front end: encoder (+stats), ln folded into the bottleneck's operand load
-    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, slot(0), B, l.A, T, l.N, l.K, L, st));
-    else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, st));
+    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
+    else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
     {
         NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)l.N * L};
         SDR_TRY(pointwise(e, ln, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
@@ -397,6 +509,21 @@ int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_pa
     const long long n = (long long)C * SAK;
     transpose_decoder_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pk + l.dec_w, pk + l.dec_wt, C, SAK);
     if (cudaGetLastError() != cudaSuccess) return SDR_ERR_CUDA;
+    if (l.causal) {
+        SDR_TRY(launch_take_taps(pk + l.enc_w, pk + l.enc_wc, (long long)l.N * l.A, 2 * l.K - 1, l.K, st));
+        if (l.bn_pk) SDR_TRY(pack_pointwise_mma(pk + l.bn_w, l.Co, l.N, pk + l.bn_pk, st));
+        for (int i = 0; i < l.U; ++i) {
+            const CausalBlockOff& u = l.cb[i];
+            SDR_TRY(launch_scale_by_scalar(pk + u.res_w, pk + u.gain, pk + u.res_wg, (long long)l.Co * l.Ci, st));
+            SDR_TRY(launch_scale_by_scalar(pk + u.res_b, pk + u.gain, pk + u.res_bg, l.Co, st));
+            if (u.proj_pk) SDR_TRY(pack_pointwise_mma(pk + u.proj_w, l.Ci, l.Co, pk + u.proj_pk, st));
+            if (u.res_pk) SDR_TRY(pack_pointwise_mma(pk + u.res_wg, l.Co, l.Ci, pk + u.res_pk, st));
+        }
+        if (l.mask_pk) SDR_TRY(pack_pointwise_mma(pk + l.mask_w, l.S * l.A * l.N, l.Co, pk + l.mask_pk, st));
+        if (l.dec_pk) SDR_TRY(pack_pointwise_mma(pk + l.dec_wt, l.S * l.A * l.K, l.S * l.A * l.N, pk + l.dec_pk, st));
+        if (l.enc_pk) SDR_TRY(pack_encoder_mma(pk + l.enc_wc, l.N, l.A, l.K, pk + l.enc_pk, st));
+        return SDR_OK;
+    }
     // bf16 hi/lo, pre-swizzled tensor-core images of every eligible 1x1 weight
     if (l.bn_pk) SDR_TRY(pack_pointwise_mma(pk + l.bn_w, l.Co, l.N, pk + l.bn_pk, st));
     for (int i = 0; i < l.U; ++i) {
@@ -423,6 +550,7 @@ static int check_forward_args(const Layout& l, int B, int64_t T) {
         if (!(n == 4 || n == 8 || n == 16 || n == 32) || l.G > 16) return SDR_ERR_UNSUPPORTED;
     }
     if (padded_len(l, T) / l.hop > 0x3fffffffLL) return SDR_ERR_UNSUPPORTED;
+    if (l.causal && !causal_pyramid_eligible(l.D, (int)(padded_len(l, T) / l.hop))) return SDR_ERR_UNSUPPORTED;
     return SDR_OK;
 }
 
@@ -443,6 +571,7 @@ int sdr_forward(const sdr_config* cfg, const void* packed, const float* mixture,
 static int launch_count(const Layout& l, long long T) {
     // encoder + bottleneck + U * (proj + levels + merge + res [+ tac (+ tac_apply unless it is folded into proj)])
     // + mask + decoder GEMM + overlap-add; levels = pyramid + solve when the one-pass path takes the shape, else D launches
+    if (l.causal) return 2 + 3 * l.U + 3;      // encoder, bottleneck, U x (proj, depthwise pyramid, res), mask, decoder, overlap-add
     const bool folded = l.gc && l.U > 0 && !l.ub[0].proj_pk && l.cob <= 64 && l.cib <= 64 && l.D >= 2;   // L % 4 == 0 then
     const int L = (int)(padded_len(l, T) / l.hop);
     const int levels = pyramid_eligible(l.D, l.cib, L) ? 2 : l.D;
@@ -498,7 +627,7 @@ int sdr_encoder(const float* wav, const float* weight, float* enc, double* stats
                 int B, int A, int64_t T, int N, int K, int L, sdr_stream stream) {
     if (!wav || !weight || !enc || !stats) return SDR_ERR_BAD_ARGUMENT;
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
-    return launch_encoder(wav, weight, enc, stats, B, A, T, N, K, L, static_cast<cudaStream_t>(stream));
+    return launch_encoder(wav, weight, enc, stats, B, A, T, N, K, L, K / 2, static_cast<cudaStream_t>(stream));
 }
 
 size_t sdr_encoder_mma_packed_bytes(int N, int A, int K) { return encoder_mma_packed_bytes(N, A, K); }
@@ -512,7 +641,7 @@ int sdr_encoder_mma_pack(const float* weight, int N, int A, int K, void* packed,
 int sdr_encoder_mma(const float* wav, const void* packed_w, float* enc, double* stats,
                     int B, int A, int64_t T, int N, int K, int L, sdr_stream stream) {
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
-    return launch_encoder_mma(wav, packed_w, enc, stats, B, A, T, N, K, L, static_cast<cudaStream_t>(stream));
+    return launch_encoder_mma(wav, packed_w, enc, stats, B, A, T, N, K, L, K / 2, static_cast<cudaStream_t>(stream));
 }
 
 int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const float* bias,
@@ -572,6 +701,11 @@ int sdr_merge_pyramid(const float* const* z, const void* scratch, int D, float* 
     const char* sc = static_cast<const char*>(scratch);
     return launch_merge_pyramid(z, reinterpret_cast<const float*>(sc + pyr_table_offset(samples, C, D)), D, m, stats_out,
                                 samples, C, L, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_causal_pyramid(const float* y, const float* slope_in, const float* const* w21, const float* const* bias,
+                       const float* const* slope, float* m, int D, int samples, int C, int L, sdr_stream stream) {
+    return launch_causal_pyramid(y, slope_in, w21, bias, slope, m, D, samples, C, L, static_cast<cudaStream_t>(stream));
 }
 
 int sdr_merge(const float* const* z, const sdr_norm_in* fins, int depth, float* m, double* stats_out,

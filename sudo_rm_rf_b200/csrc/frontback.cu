@@ -14,7 +14,7 @@
 namespace sdr {
 
 // ---------------------------------------------------------------------------
-// encoder: enc[b,n,t] = sum_a sum_j w[n,a,j] * wav[b,a, hop*t + j - hop]
+// encoder: enc[b,n,t] = sum_a sum_j w[n,a,j] * wav[b,a, hop*t + j - pad]
 // CTA = 128 positions x kEncNB basis functions; the waveform chunk and the
 // weight slab sit in shared memory; each thread owns one position and walks the
 // basis functions four at a time (weights read as broadcast float4).
@@ -25,7 +25,7 @@ constexpr int kEncNB = 64;
 __global__ void __launch_bounds__(kEncThreads)
 encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight,
                float* __restrict__ enc, double* __restrict__ stats,
-               int A, long long T, int N, int K, int L, int t_tiles) {
+               int A, long long T, int N, int K, int L, int t_tiles, int pad) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_red[64];
     const int hop = K / 2;
@@ -38,7 +38,7 @@ encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight,
     const int n0 = blockIdx.y * kEncNB;
     const int tid = threadIdx.x;
 
-    const long long base = (long long)hop * t0 - hop;      // first sample index of the chunk
+    const long long base = (long long)hop * t0 - pad;      // first sample index of the chunk (pad = hop; 2 * hop for the causal model)
     for (int i = tid; i < A * span; i += kEncThreads) {
         const int a = i / span, p = i - a * span;
         const long long g = base + p;
@@ -78,11 +78,11 @@ encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight,
             }
         }
     }
-    block_stats_atomic(st_s, st_q, stats, b, s_red);
+    if (stats) block_stats_atomic(st_s, st_q, stats, b, s_red);
 }
 
 int launch_encoder(const float* wav, const float* weight, float* enc, double* stats,
-                   int B, int A, long long T, int N, int K, int L, cudaStream_t st) {
+                   int B, int A, long long T, int N, int K, int L, int pad, cudaStream_t st) {
     if (B <= 0 || A <= 0 || T <= 0 || N <= 0 || K < 3 || L <= 0) return SDR_ERR_BAD_ARGUMENT;
     const int hop = K / 2;
     const int span = hop * (kEncThreads - 1) + K;
@@ -96,7 +96,7 @@ int launch_encoder(const float* wav, const float* weight, float* enc, double* st
     const long long gx = (long long)t_tiles * B;
     if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)gx, (unsigned)((N + kEncNB - 1) / kEncNB));
-    encoder_kernel<<<grid, kEncThreads, smem, st>>>(wav, weight, enc, stats, A, T, N, K, L, t_tiles);
+    encoder_kernel<<<grid, kEncThreads, smem, st>>>(wav, weight, enc, stats, A, T, N, K, L, t_tiles, pad);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

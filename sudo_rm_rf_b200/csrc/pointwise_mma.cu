@@ -1269,7 +1269,7 @@ int pack_encoder_mma(const float* W, int N, int A, int Kk, void* packed, cudaStr
 }
 
 int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* stats,
-                       int B, int A, long long T, int N, int Kk, int L, cudaStream_t st) {
+                       int B, int A, long long T, int N, int Kk, int L, int pad, cudaStream_t st) {
     if (!encoder_mma_packed_bytes(N, A, Kk)) return SDR_ERR_UNSUPPORTED;
     if (B <= 0 || T <= 0 || L <= 0 || !wav || !wpk || !enc) return SDR_ERR_BAD_ARGUMENT;
     MmaArgs a;
@@ -1280,7 +1280,7 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
 #if SDR_MMA_TRACE
     a.trace = nullptr;
 #endif
-    a.win_k = Kk; a.win_hop = Kk / 2; a.win_pad = Kk / 2; a.win_a = A; a.win_T = T;
+    a.win_k = Kk; a.win_hop = Kk / 2; a.win_pad = pad; a.win_a = A; a.win_T = T;   // pad = hop; 2 * hop for the causal model
     a.tile_n = mma_tile_n(N);
     a.n_tiles = mma_pad_m(N) / a.tile_n;
     a.l_tiles = (L + kTileM - 1) / kTileM;

@@ -28,6 +28,7 @@ warnings.filterwarnings("ignore")
 
 import sudo_rm_rf.dnn.models.improved_sudormrf as ref_improved            # noqa: E402
 import sudo_rm_rf.dnn.models.groupcomm_sudormrf_v2 as ref_gc              # noqa: E402
+import sudo_rm_rf.dnn.models.causal_improved_sudormrf_v3 as ref_causal    # noqa: E402
 import sudo_rm_rf.dnn.experiments.utils.mixture_consistency as ref_mc     # noqa: E402
 from oracle import sudormrf_oracle as O                                    # noqa: E402
 
@@ -57,6 +58,15 @@ CASES = [
      dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=3,
           enc_kernel_size=11, enc_num_basis=16, num_sources=2, group_size=8,
           in_audio_channels=2), 2, 333, "randn"),
+    ("causal_small_odd", "causal",           # causal_improved_sudormrf_v3.py: masked 21-tap depthwise, no norms
+     dict(in_audio_channels=1, out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+          enc_kernel_size=21, enc_num_basis=48, num_sources=2), 2, 1003, "randn"),
+    ("causal_stereo", "causal",              # in_audio_channels=2, other kernel size, depth 5, short input (T < hop*2^D)
+     dict(in_audio_channels=2, out_channels=16, in_channels=32, num_blocks=3, upsampling_depth=5,
+          enc_kernel_size=11, enc_num_basis=24, num_sources=3), 2, 131, "rand"),
+    ("causal_default_init", "causal",        # the reference ctor's own init (skipinit_gain = 0: every block the identity)
+     dict(in_audio_channels=1, out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=3,
+          enc_kernel_size=21, enc_num_basis=32, num_sources=2), 2, 801, "randn"),
 ]
 
 HOOKS = ["encoder", "bottleneck", "sm.0.proj_1x1.conv", "sm.0.spp_dw.0.conv",
@@ -66,12 +76,16 @@ HOOKS = ["encoder", "bottleneck", "sm.0.proj_1x1.conv", "sm.0.spp_dw.0.conv",
 
 
 def main():
+    only = sys.argv[1:]                      # optional name prefixes: regenerate a subset, leave the other fixtures alone
     for idx, (name, variant, kw, B, T, kind) in enumerate(CASES):
+        if only and not any(name.startswith(o) for o in only):
+            continue
         torch.manual_seed(100 + idx)
-        cls = ref_improved.SuDORMRF if variant == "improved" else ref_gc.GroupCommSudoRmRf
+        cls = {"improved": ref_improved.SuDORMRF, "groupcomm": ref_gc.GroupCommSudoRmRf,
+               "causal": ref_causal.CausalSuDORMRF}[variant]
         model = cls(**kw).eval()
         cfg = O.Config(variant=variant, **kw)
-        if name != "improved_default_init":
+        if not name.endswith("default_init"):
             model.load_state_dict(O.make_state_dict(cfg, seed=7 + idx, perturbed=True))
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         A = kw.get("in_audio_channels", 1)

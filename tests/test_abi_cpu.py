@@ -39,9 +39,13 @@ def test_header_symbols_are_exported():
     ("groupcomm", dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=3,
                        enc_kernel_size=11, enc_num_basis=16, num_sources=2, group_size=8,
                        in_audio_channels=2)),
+    ("causal", dict(in_audio_channels=1, out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+                    enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
+    ("causal", dict(in_audio_channels=2, out_channels=16, in_channels=32, num_blocks=3, upsampling_depth=5,
+                    enc_kernel_size=11, enc_num_basis=24, num_sources=3)),
 ])
 def test_layout_matches_state_dict(variant, kw):
-    cls = P.SuDORMRF if variant == "improved" else P.GroupCommSudoRmRf
+    cls = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}[variant]
     m = cls(**kw)
     cfg_o = O.Config(variant=variant, **kw)
     sd = m.state_dict()

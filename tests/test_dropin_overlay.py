@@ -53,8 +53,9 @@ ref = {reference!r}
 assert improved_sudormrf.SuDORMRF is P.SuDORMRF, improved_sudormrf.__file__
 assert sudormrf_gc_v2.GroupCommSudoRmRf is P.GroupCommSudoRmRf
 assert mixture_consistency.apply is P.mixture_consistency.apply
+assert causal.CausalSuDORMRF is P.CausalSuDORMRF
 # everything else -> the reference's own files
-for mod in (parser, sisdr_lib, initial_sudormrf, causal, snr_lib):
+for mod in (parser, sisdr_lib, initial_sudormrf, snr_lib):
     assert mod.__file__.startswith(ref), mod.__file__
 # the objects the runner builds from them (run_improved_sudormrf.py:66-70,82-85,88-96)
 loss = sisdr_lib.PermInvariantSISDR(batch_size=2, n_sources=2, zero_mean=True, backward_loss=False,
@@ -86,7 +87,7 @@ def test_overlay_keeps_rest_of_reference_importable():
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
 def test_meta_path_redirect_with_reference_first():
-    """`sudo_rm_rf_b200.dropin.install()`: reference FIRST on sys.path, only the three names are redirected."""
+    """`sudo_rm_rf_b200.dropin.install()`: reference FIRST on sys.path, only the accelerated names are redirected."""
     setup = (f"sys.path.insert(0, {REPO!r}); sys.path.insert(0, {REFERENCE!r})\n"
              "import sudo_rm_rf_b200.dropin as D; D.install()")
     assert "runner imports ok" in _run(RUNNER_IMPORTS.format(setup=setup, reference=REFERENCE))

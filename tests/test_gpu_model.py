@@ -15,9 +15,11 @@ DEV = "cuda"
 TOL = 1e-3
 
 
+CLASSES = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}
+
+
 def build(variant, kw, sd):
-    cls = P.SuDORMRF if variant == "improved" else P.GroupCommSudoRmRf
-    m = cls(**kw)
+    m = CLASSES[variant](**kw)
     m.load_state_dict(sd)
     return m.to(DEV).eval()
 
@@ -81,6 +83,14 @@ FULL = [
     ("cfg4_groupcomm_u8_512_T31999", "groupcomm",
      dict(out_channels=256, in_channels=512, num_blocks=8, upsampling_depth=5,
           enc_kernel_size=21, enc_num_basis=512, num_sources=2, group_size=16), 1, 31999),
+    # SURVEY 8f.3 sibling variant: CausalSuDORMRF with its constructor defaults (causal_improved_sudormrf_v3.py:121-129)
+    # and the stereo / depth-5 geometry of its __main__ block (:235-243), odd length
+    ("causal_default_u16_512", "causal",
+     dict(in_audio_channels=1, out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+          enc_kernel_size=21, enc_num_basis=512, num_sources=2), 2, 32000),
+    ("causal_stereo_u4_512_T44099", "causal",
+     dict(in_audio_channels=2, out_channels=256, in_channels=512, num_blocks=4, upsampling_depth=5,
+          enc_kernel_size=21, enc_num_basis=512, num_sources=2), 1, 44099),
 ]
 DEFAULT_TOO = ("cfg2_improved_u16_512", "cfg3_improved_u36_2048", "cfg5_improved_u36_4096_16k")
 
@@ -93,7 +103,7 @@ def test_full_size_vs_oracle(name, variant, kw, B, T, weights):
     cfg = O.Config(variant=variant, **kw)
     sd = O.make_state_dict(cfg, seed=21, perturbed=(weights == "perturbed"))
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(B, 1, T, generator=g)
+    x = torch.randn(B, kw.get("in_audio_channels", 1), T, generator=g)
     x = (x - x.mean(-1, keepdim=True)) / (x.std(-1, keepdim=True) + 1e-9)   # README.md:101-103
     ref = O.forward(cfg, sd, x)
     m = build(variant, kw, sd)

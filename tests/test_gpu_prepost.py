@@ -20,7 +20,7 @@ TOL = 1e-3
 
 
 def build(variant, kw, sd):
-    cls = P.SuDORMRF if variant == "improved" else P.GroupCommSudoRmRf
+    cls = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}[variant]
     m = cls(**kw)
     m.load_state_dict(sd)
     return m.to(DEV).eval()

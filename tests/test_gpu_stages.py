@@ -134,6 +134,44 @@ def test_depthwise_pyramid(samples, C_, L, D, prelu):
     assert lib.sdr_pyramid_scratch_bytes(samples, C_, 6, 96) == 0
 
 
+@pytest.mark.parametrize("samples,C_,L,D", [
+    (2, 32, 3200, 4), (2, 32, 3200, 5), (1, 512, 3200, 4), (3, 7, 64, 5), (2, 5, 32, 5), (2, 9, 16, 2), (2, 4, 8, 1),
+    (2, 16, 6400, 6), (1, 8, 4096, 4), (1, 8, 4160, 5), (2, 6, 256, 8), (2, 3, 48, 4),
+])
+def test_causal_pyramid(samples, C_, L, D):
+    """sdr_causal_pyramid == PReLU -> D x (masked 21-tap depthwise conv + PReLU) -> upsample/add chain in torch
+    (causal_improved_sudormrf_v3.py:106-116, mask :21-27)."""
+    lib = N.lib()
+    g = torch.Generator().manual_seed(13)
+    y = (torch.randn(samples, C_, L, generator=g) * 1.3 + 0.1).to(DEV)
+    sp = torch.tensor([0.3], device=DEV)
+    ws = [torch.randn(C_, 1, 21, generator=g).to(DEV) * 0.4 for _ in range(D)]
+    bs = [torch.randn(C_, generator=g).to(DEV) * 0.5 for _ in range(D)]
+    sl = [torch.tensor([0.1 + 0.07 * d], device=DEV) for d in range(D)]
+    m = torch.full((samples, C_, L), float("nan"), device=DEV)
+    arr = lambda ts: (C.c_void_p * D)(*[t.data_ptr() for t in ts])
+    N.check(lib.sdr_causal_pyramid(p(y), p(sp), arr(ws), arr(bs), arr(sl), p(m), D, samples, C_, L, stream()))
+    cur = O.prelu1(y, sp)
+    levels = []
+    for d in range(D):
+        cur = O.prelu1(F.conv1d(cur, O.causal_weight(ws[d]), bs[d], stride=1 if d == 0 else 2, padding=10, groups=C_),
+                       sl[d])
+        levels.append(cur)
+    for _ in range(D - 1):
+        top = levels.pop()
+        levels[-1] = levels[-1] + F.interpolate(top, scale_factor=2, mode="nearest")
+    close(m, levels[0])
+    # causality: the first half of the output does not depend on the second half of the input
+    y2 = y.clone()
+    y2[..., L // 2:] = 7.0
+    m2 = torch.empty_like(m)
+    N.check(lib.sdr_causal_pyramid(p(y2), p(sp), arr(ws), arr(bs), arr(sl), p(m2), D, samples, C_, L, stream()))
+    assert torch.equal(m2[..., :L // 2], m[..., :L // 2])
+    # lengths that do not halve D times are refused, not mis-computed
+    assert lib.sdr_causal_pyramid(p(y), p(sp), arr(ws), arr(bs), arr(sl), p(m), D, samples, C_, L - 4, stream()) == -5 \
+        or (L - 4) % (1 << D) == 0
+
+
 @pytest.mark.parametrize("samples,C_,L,depth", [
     (2, 32, 3200, 5), (3, 16, 64, 6), (2, 8, 32, 1), (2, 5, 2, 1), (2, 6, 6, 2), (1, 512, 3200, 5),
     (2, 8, 48, 4), (2, 7, 128, 8), (3, 5, 24, 4), (2, 512, 6400, 6),
