@@ -12,6 +12,7 @@ reference tree (``/root/reference``):
   improved_sudormrf.py   = sudo_rm_rf/dnn/models/improved_sudormrf.py
   groupcomm_sudormrf_v2.py = sudo_rm_rf/dnn/models/groupcomm_sudormrf_v2.py
   causal_improved_sudormrf_v3.py = sudo_rm_rf/dnn/models/causal_improved_sudormrf_v3.py
+  sudormrf.py            = sudo_rm_rf/dnn/models/sudormrf.py (the original SuDoRM-RF, variant "original")
   mixture_consistency.py = sudo_rm_rf/dnn/experiments/utils/mixture_consistency.py
   README.md              = the reference's README (inference recipe, lines 100-114)
   sisdr.py               = sudo_rm_rf/dnn/losses/sisdr.py (validation metric)
@@ -47,9 +48,10 @@ class Config:
 
     improved_sudormrf.py:224-231 (SuDORMRF),
     groupcomm_sudormrf_v2.py:232-241 (GroupCommSudoRmRf) and
-    causal_improved_sudormrf_v3.py:121-129 (CausalSuDORMRF).
+    causal_improved_sudormrf_v3.py:121-129 (CausalSuDORMRF),
+    sudormrf.py:186-193 (the original SuDORMRF).
     """
-    variant: str = "improved"          # "improved" | "groupcomm" | "causal"
+    variant: str = "improved"          # "improved" | "groupcomm" | "causal" | "original"
     out_channels: int = 128
     in_channels: int = 512
     num_blocks: int = 16
@@ -75,7 +77,11 @@ class Config:
 
 def padded_length(cfg: Config, T: int) -> int:
     """improved_sudormrf.py:303-310: round T up to a multiple of hop*2^D
-    (at least one multiple)."""
+    (at least one multiple).  The original model (sudormrf.py:206-209,283-293) rounds up to a multiple of
+    lcm(hop, 2^D) instead and leaves a length that already is one alone."""
+    if cfg.variant == "original":
+        q = cfg.hop * 2 ** cfg.upsampling_depth // math.gcd(cfg.hop, 2 ** cfg.upsampling_depth)
+        return T if T % q == 0 else T + q - T % q
     q = cfg.n_least_samples_req
     if T < q:
         return q
@@ -113,6 +119,8 @@ def param_shapes(cfg: Config) -> Dict[str, tuple]:
     S, D, k = cfg.num_sources, cfg.upsampling_depth, cfg.enc_kernel_size
     if cfg.variant == "causal":
         return _causal_param_shapes(cfg)
+    if cfg.variant == "original":
+        return _original_param_shapes(cfg)
     A = cfg.in_audio_channels if cfg.variant == "groupcomm" else 1
     s: Dict[str, tuple] = {}
     s["encoder.weight"] = (N, A, k)                  # improved_sudormrf.py:247-251
@@ -174,6 +182,59 @@ def _causal_param_shapes(cfg: Config) -> Dict[str, tuple]:
     return s
 
 
+def _original_param_shapes(cfg: Config) -> Dict[str, tuple]:
+    """sudormrf.py:211-264 (model), :134-157 (UBlock): GroupNorm(1, C) norms (``weight`` / ``bias``), one PReLU
+    slope per channel, a biased encoder and decoder, a ``conv_1x1_exp`` + ``module_act`` tail in every block, the
+    (N+1) x 1 Conv2d that produces the mask logits, a grouped decoder, and ``ln_mask_in`` (registered last, :264,
+    never used by forward)."""
+    N, Co, Ci = cfg.enc_num_basis, cfg.out_channels, cfg.in_channels
+    S, D, k = cfg.num_sources, cfg.upsampling_depth, cfg.enc_kernel_size
+    s: Dict[str, tuple] = {}
+    s["encoder.0.weight"] = (N, 1, k)                # :212-218
+    s["encoder.0.bias"] = (N,)
+    s["ln.weight"] = (N,)                            # :221
+    s["ln.bias"] = (N,)
+    s["l1.weight"] = (Co, N, 1)                      # :222-224
+    s["l1.bias"] = (Co,)
+    for i in range(cfg.num_blocks):
+        p = f"sm.{i}."
+        s[p + "proj_1x1.conv.weight"] = (Ci, Co, 1)  # :138-139
+        s[p + "proj_1x1.conv.bias"] = (Ci,)
+        s[p + "proj_1x1.norm.weight"] = (Ci,)
+        s[p + "proj_1x1.norm.bias"] = (Ci,)
+        s[p + "proj_1x1.act.weight"] = (Ci,)
+        for d in range(D):                           # :141-154
+            s[p + f"spp_dw.{d}.conv.weight"] = (Ci, 1, 5)
+            s[p + f"spp_dw.{d}.conv.bias"] = (Ci,)
+            s[p + f"spp_dw.{d}.norm.weight"] = (Ci,)
+            s[p + f"spp_dw.{d}.norm.bias"] = (Ci,)
+        s[p + "conv_1x1_exp.conv.weight"] = (Co, Ci, 1)   # :160
+        s[p + "conv_1x1_exp.conv.bias"] = (Co,)
+        s[p + "conv_1x1_exp.norm.weight"] = (Co,)
+        s[p + "conv_1x1_exp.norm.bias"] = (Co,)
+        s[p + "final_norm.norm.weight"] = (Ci,)      # :161
+        s[p + "final_norm.norm.bias"] = (Ci,)
+        s[p + "final_norm.act.weight"] = (Ci,)
+        s[p + "module_act.norm.weight"] = (Co,)      # :162
+        s[p + "module_act.norm.bias"] = (Co,)
+        s[p + "module_act.act.weight"] = (Co,)
+    if Co != N:                                      # :233-236
+        s["reshape_before_masks.weight"] = (N, Co, 1)
+        s["reshape_before_masks.bias"] = (N,)
+    s["m.weight"] = (S, 1, N + 1, 1)                 # :239-242
+    s["m.bias"] = (S,)
+    s["decoder.weight"] = (N * S, 1, k)              # :245-252 (groups = S)
+    s["decoder.bias"] = (S,)
+    s["ln_mask_in.weight"] = (N,)                    # :253
+    s["ln_mask_in.bias"] = (N,)
+    return s
+
+
+def _is_groupnorm(name: str, leaf: str) -> bool:
+    """GroupNorm parameters of the original model (``weight`` = gamma, ``bias`` = beta)."""
+    return name.endswith("norm." + leaf) or name in ("ln." + leaf, "ln_mask_in." + leaf)
+
+
 def make_state_dict(cfg: Config, seed: int = 0, perturbed: bool = True,
                     dtype=torch.float32) -> Dict[str, Tensor]:
     """Seeded synthetic weights with the reference's names and shapes.
@@ -191,9 +252,9 @@ def make_state_dict(cfg: Config, seed: int = 0, perturbed: bool = True,
             # the residual stream O(1) while making every block matter
             t = 0.5 + 0.2 * torch.rand(shape, generator=g) if perturbed else torch.zeros(shape)
         elif not perturbed:
-            if name.endswith("gamma"):
+            if name.endswith("gamma") or _is_groupnorm(name, "weight"):
                 t = torch.ones(shape)
-            elif name.endswith("beta"):
+            elif name.endswith("beta") or _is_groupnorm(name, "bias"):
                 t = torch.zeros(shape)
             elif name.endswith("act.weight") or name in ("mask_net.0.weight", "mask_nl_class.weight") or \
                     (name.endswith(".1.weight") and "TAC" in name):
@@ -202,10 +263,15 @@ def make_state_dict(cfg: Config, seed: int = 0, perturbed: bool = True,
                 fan_in = max(1, int(math.prod(shape[1:])))
                 t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
         else:
-            if name.endswith("gamma"):
+            if name.endswith("gamma") or _is_groupnorm(name, "weight"):
                 t = 1.0 + 0.3 * torch.randn(shape, generator=g)
-            elif name.endswith("beta"):
+            elif name.endswith("beta") or _is_groupnorm(name, "bias"):
                 t = 0.2 * torch.randn(shape, generator=g)
+            elif name.endswith("act.weight") and len(shape) == 1 and shape[0] > 1:
+                # per-channel PReLU slopes: most in [0.1, 0.6), about a tenth negative and a seventh above 1
+                r = torch.rand(shape, generator=g)
+                t = 0.1 + 0.5 * torch.rand(shape, generator=g)
+                t = torch.where(r < 0.1, torch.full_like(t, -0.2), torch.where(r > 0.85, torch.full_like(t, 1.3), t))
             elif len(shape) == 1 and shape[0] == 1:
                 t = 0.25 + 0.15 * torch.rand(shape, generator=g)   # PReLU slopes
             elif len(shape) == 1:
@@ -337,6 +403,8 @@ def forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor,
     """
     if cfg.variant == "causal":
         return causal_forward(cfg, sd, wav, taps=taps, dtype=dtype)
+    if cfg.variant == "original":
+        return original_forward(cfg, sd, wav, taps=taps, dtype=dtype)
     if wav.dim() != 3:
         raise RuntimeError("expected a 3-D input [batch, audio_channels, time]")
     sd = {k: v.to(device=wav.device, dtype=dtype) for k, v in sd.items()}   # (bench.py times this op sequence on cuda too)
@@ -434,6 +502,91 @@ def causal_forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor, taps: Option
     x = prelu1(x, sd["mask_nl_class.weight"])                                                   # :206 (no product with the encoder output, :207)
     y = F.conv_transpose1d(x, sd["decoder.weight"], None, stride=hop, padding=hop, output_padding=hop - 1)   # :209
     return y[..., :T]                                                                           # :210
+
+
+def prelu_c(x: Tensor, slope: Tensor) -> Tensor:
+    """nn.PReLU(C): one slope per channel (sudormrf.py:33,71)."""
+    return torch.where(x >= 0, x, x * slope.view(1, -1, 1))
+
+
+def original_ublock(x: Tensor, sd: Dict[str, Tensor], p: str, depth: int, taps: Optional[dict] = None) -> Tensor:
+    """UBlock.forward, sudormrf.py:164-185.  GroupNorm(1, C, eps=1e-8) (:32,56,70,117) normalises over (C, L) with
+    the biased variance and the eps inside the square root, i.e. the arithmetic of ``glob_ln``.
+
+    y   = PReLU_c(GN(W1 x + b1))                               (:171)
+    z_0 = GN(dw5_s1(y)), z_d = GN(dw5_s2(z_{d-1}))             (:172-177)
+    m   = z_0 + up2(z_1 + up2(z_2 + ...))  (nearest)           (:180-182)
+    e   = GN(Wexp PReLU_c(GN(m)) + bexp)                       (:184)
+    out = PReLU_c(GN(e + x))                                   (:186)
+    """
+    ci = sd[p + "proj_1x1.conv.weight"].shape[0]
+    y = F.conv1d(x, sd[p + "proj_1x1.conv.weight"], sd[p + "proj_1x1.conv.bias"])
+    if taps is not None:
+        taps[p + "proj_1x1.conv"] = y
+    y = prelu_c(glob_ln(y, sd[p + "proj_1x1.norm.weight"], sd[p + "proj_1x1.norm.bias"]), sd[p + "proj_1x1.act.weight"])
+    levels = []
+    cur = y
+    for d in range(depth):
+        z = F.conv1d(cur, sd[p + f"spp_dw.{d}.conv.weight"], sd[p + f"spp_dw.{d}.conv.bias"],
+                     stride=1 if d == 0 else 2, padding=2, groups=ci)       # :141-154: 5 taps at every level
+        if taps is not None:
+            taps[p + f"spp_dw.{d}.conv"] = z
+        cur = glob_ln(z, sd[p + f"spp_dw.{d}.norm.weight"], sd[p + f"spp_dw.{d}.norm.bias"])
+        levels.append(cur)
+    for _ in range(depth - 1):
+        top = levels.pop()
+        levels[-1] = levels[-1] + F.interpolate(top, scale_factor=2, mode="nearest")
+    m = levels[0]
+    if taps is not None:
+        taps[p + "merge"] = m
+    e = prelu_c(glob_ln(m, sd[p + "final_norm.norm.weight"], sd[p + "final_norm.norm.bias"]),
+                sd[p + "final_norm.act.weight"])
+    e = F.conv1d(e, sd[p + "conv_1x1_exp.conv.weight"], sd[p + "conv_1x1_exp.conv.bias"])
+    if taps is not None:
+        taps[p + "conv_1x1_exp.conv"] = e
+    u = glob_ln(e, sd[p + "conv_1x1_exp.norm.weight"], sd[p + "conv_1x1_exp.norm.bias"]) + x
+    if taps is not None:
+        taps[p + "sum"] = u
+    out = prelu_c(glob_ln(u, sd[p + "module_act.norm.weight"], sd[p + "module_act.norm.bias"]),
+                  sd[p + "module_act.act.weight"])
+    if taps is not None:
+        taps[p + "out"] = out
+    return out
+
+
+def original_forward(cfg: Config, sd: Dict[str, Tensor], wav: Tensor, taps: Optional[dict] = None,
+                     dtype=torch.float32) -> Tensor:
+    """SuDORMRF.forward of the ORIGINAL model, sudormrf.py:266-291.  wav [B, 1, T] -> [B, S, T]."""
+    if wav.dim() != 3:
+        raise RuntimeError("expected a 3-D input [batch, 1, time]")
+    sd = {k: v.to(device=wav.device, dtype=dtype) for k, v in sd.items()}
+    T = wav.shape[-1]
+    hop, S, N = cfg.hop, cfg.num_sources, cfg.enc_num_basis
+    x = pad_wave(cfg, wav, dtype)                                                               # :268, :283-293
+    x = torch.relu(F.conv1d(x, sd["encoder.0.weight"], sd["encoder.0.bias"], stride=hop, padding=hop))   # :269
+    if taps is not None:
+        taps["encoder"] = x
+    s = x                                                                                       # :272
+    x = glob_ln(x, sd["ln.weight"], sd["ln.bias"])                                              # :275
+    x = F.conv1d(x, sd["l1.weight"], sd["l1.bias"])                                             # :276
+    if taps is not None:
+        taps["l1"] = x
+    for i in range(cfg.num_blocks):                                                             # :277
+        x = original_ublock(x, sd, f"sm.{i}.", cfg.upsampling_depth, taps)
+    if cfg.out_channels != N:                                                                   # :279-281
+        x = F.conv1d(x, sd["reshape_before_masks.weight"], sd["reshape_before_masks.bias"])
+        if taps is not None:
+            taps["reshape_before_masks"] = x
+    x = F.conv2d(x.unsqueeze(1), sd["m.weight"], sd["m.bias"], padding=(N - N // 2, 0))         # :284, :239-242
+    if taps is not None:
+        taps["m"] = x
+    x = torch.sigmoid(x) if S == 1 else torch.softmax(x, dim=1)                                 # :285-288
+    x = x * s.unsqueeze(1)                                                                      # :289
+    if taps is not None:
+        taps["masked"] = x.reshape(x.shape[0], -1, x.shape[-1])
+    y = F.conv_transpose1d(x.reshape(x.shape[0], -1, x.shape[-1]), sd["decoder.weight"], sd["decoder.bias"],
+                           stride=hop, padding=hop, output_padding=hop - 1, groups=S)           # :291, :245-252
+    return y[..., :T]                                                                           # :292
 
 
 def mixture_consistency(est: Tensor, mix: Tensor,

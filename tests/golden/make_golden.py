@@ -29,6 +29,7 @@ warnings.filterwarnings("ignore")
 import sudo_rm_rf.dnn.models.improved_sudormrf as ref_improved            # noqa: E402
 import sudo_rm_rf.dnn.models.groupcomm_sudormrf_v2 as ref_gc              # noqa: E402
 import sudo_rm_rf.dnn.models.causal_improved_sudormrf_v3 as ref_causal    # noqa: E402
+import sudo_rm_rf.dnn.models.sudormrf as ref_original                      # noqa: E402
 import sudo_rm_rf.dnn.experiments.utils.mixture_consistency as ref_mc     # noqa: E402
 from oracle import sudormrf_oracle as O                                    # noqa: E402
 
@@ -67,12 +68,25 @@ CASES = [
     ("causal_default_init", "causal",        # the reference ctor's own init (skipinit_gain = 0: every block the identity)
      dict(in_audio_channels=1, out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=3,
           enc_kernel_size=21, enc_num_basis=32, num_sources=2), 2, 801, "randn"),
+    # the original SuDoRM-RF (sudormrf.py): GroupNorm, per-channel PReLU, Conv2d + softmax masks, grouped decoder
+    ("original_small_odd", "original",       # out_channels != enc_num_basis: reshape_before_masks exists
+     dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=3,
+          enc_kernel_size=21, enc_num_basis=24, num_sources=2), 2, 517, "randn"),
+    ("original_three_src", "original",       # out_channels == enc_num_basis (no reshape layer), T a multiple of the lcm
+     dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+          enc_kernel_size=21, enc_num_basis=32, num_sources=3), 2, 800, "rand"),
+    ("original_sigmoid", "original",         # one source: sigmoid instead of softmax (:285-286); other kernel size
+     dict(out_channels=32, in_channels=64, num_blocks=1, upsampling_depth=4,
+          enc_kernel_size=11, enc_num_basis=16, num_sources=1), 1, 333, "randn"),
+    ("original_default_init", "original",    # the reference ctor's own init
+     dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=4,
+          enc_kernel_size=21, enc_num_basis=32, num_sources=2), 2, 801, "randn"),
 ]
 
 HOOKS = ["encoder", "bottleneck", "sm.0.proj_1x1.conv", "sm.0.spp_dw.0.conv",
          "sm.0.spp_dw.1.conv", "sm.0.final_norm.norm", "sm.0", "sm.1",
          "sm.0.UBlock.proj_1x1.conv", "sm.0.UBlock.spp_dw.1.conv", "sm.0.TAC",
-         "mask_net.1", "decoder"]
+         "mask_net.1", "decoder", "l1", "sm.0.conv_1x1_exp.conv", "m"]
 
 
 def main():
@@ -82,7 +96,7 @@ def main():
             continue
         torch.manual_seed(100 + idx)
         cls = {"improved": ref_improved.SuDORMRF, "groupcomm": ref_gc.GroupCommSudoRmRf,
-               "causal": ref_causal.CausalSuDORMRF}[variant]
+               "causal": ref_causal.CausalSuDORMRF, "original": ref_original.SuDORMRF}[variant]
         model = cls(**kw).eval()
         cfg = O.Config(variant=variant, **kw)
         if not name.endswith("default_init"):

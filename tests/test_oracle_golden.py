@@ -35,7 +35,8 @@ def test_forward_matches_reference_golden(golden):
                 "sm.0.spp_dw.1.conv": "sm.0.spp_dw.1.conv",
                 "sm.0.UBlock.proj_1x1.conv": "sm.0.UBlock.proj_1x1.conv",
                 "sm.0.UBlock.spp_dw.1.conv": "sm.0.UBlock.spp_dw.1.conv",
-                "sm.0.TAC": "sm.0.TAC", "sm.0": "sm.0.out", "sm.1": "sm.1.out"}
+                "sm.0.TAC": "sm.0.TAC", "sm.0": "sm.0.out", "sm.1": "sm.1.out",
+                "l1": "l1", "sm.0.conv_1x1_exp.conv": "sm.0.conv_1x1_exp.conv", "m": "m"}
     checked = 0
     for ref_name, ours in name_map.items():
         if ref_name in taps:
