@@ -47,12 +47,18 @@ WORKLOADS = {
     "causal_u16_512": dict(variant="causal", B=32, T=32000, kw=dict(
         in_audio_channels=1, out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
         enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
+    # SURVEY 8f.3 sibling variant (not a BASELINE config): the ORIGINAL SuDoRM-RF with its constructor defaults
+    # (sudormrf.py:186-193) at the headline batch / length
+    "original_u16_512": dict(variant="original", B=32, T=32000, kw=dict(
+        out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+        enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
 }
 
 
 def model_class(variant):
     import sudo_rm_rf_b200 as P
-    return {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}[variant]
+    return {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF,
+            "original": P.OriginalSuDORMRF}[variant]
 METRIC = "mixtures_per_sec_forward_4s_8kHz_2src"
 UNIT = "mixtures/s"
 
@@ -97,6 +103,20 @@ def algorithmic_model(w):
         flops = 2 * L * (K * N + N * Co + U * (2 * Co * Ci + 11 * Ci * (2 - 2.0 ** (1 - D))) + Co * S * N + K * S * S * N)
         return dict(L=L, Tp=Tp, a_blk=a_blk, a_mix=a_mix, flops=flops,
                     res_bytes=4 * L * (Ci + 2 * Co), res_flops=2 * Co * Ci * L)
+    if w["variant"] == "original":
+        # sudormrf.py: lcm padding; per block two more [Co, L] tensors than the improved block (conv_1x1_exp output
+        # written + read, the residual sum written and read by two consumers): 5 Co instead of 3 Co; the back end
+        # is modelled like the improved one (block output + encoder output in, S waveforms out)
+        import math
+        q = hop * 2 ** D // math.gcd(hop, 2 ** D)
+        Tp = w["T"] if w["T"] % q == 0 else w["T"] + q - w["T"] % q
+        L = Tp // hop
+        a_blk = 4 * L * (5 * Co + kappa * Ci)
+        a_mix = 4 * (Tp + 2 * N * L + Co * L) + U * a_blk + 4 * (Co * L + N * L + S * Tp)
+        flops = 2 * L * (K * N + N * Co + U * (2 * Co * Ci + 5 * Ci * (2 - 2.0 ** (1 - D))) +
+                         (Co * N if Co != N else 0) + N * S * N + K * S * N)
+        return dict(L=L, Tp=Tp, a_blk=a_blk, a_mix=a_mix, flops=flops,
+                    res_bytes=4 * L * (Ci + Co), res_flops=2 * Co * Ci * L)
     gc = w["variant"] == "groupcomm"
     if gc:
         a_blk += 4 * L * 4 * Co
@@ -341,7 +361,8 @@ def run_b200(args, w, wl_name):
     if wl_name == "improved_u16_512" and not args.no_other_configs:
         del graph
         torch.cuda.empty_cache()
-        for name in ("improved_u36_2048", "groupcomm_u8_512", "improved_u36_4096_16k", "causal_u16_512"):
+        for name in ("improved_u36_2048", "groupcomm_u8_512", "improved_u36_4096_16k", "causal_u16_512",
+                     "original_u16_512"):
             ow, ms, n_par = short_config_run(name, dev, stream, flush)
             others.append((name, ow, n_par))
             other_ms.append(ms)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDR_ABI_VERSION 1
+#define SDR_ABI_VERSION 2
 
 /* return codes */
 #define SDR_OK                 0
@@ -40,9 +40,11 @@ extern "C" {
 /* Constructor arguments of the reference models:
  *   improved_sudormrf.py:224-231   SuDORMRF.__init__
  *   groupcomm_sudormrf_v2.py:232-241 GroupCommSudoRmRf.__init__
- *   causal_improved_sudormrf_v3.py:121-129 CausalSuDORMRF.__init__         */
+ *   causal_improved_sudormrf_v3.py:121-129 CausalSuDORMRF.__init__
+ *   sudormrf.py:186-193 SuDORMRF.__init__ (the original model)             */
 typedef struct {
-    int32_t variant;            /* 0 = improved SuDORMRF, 1 = GroupCommSudoRmRf, 2 = CausalSuDORMRF */
+    int32_t variant;            /* 0 = improved SuDORMRF, 1 = GroupCommSudoRmRf, 2 = CausalSuDORMRF,
+                                   3 = the original SuDORMRF (sudormrf.py) */
     int32_t in_audio_channels;  /* 1 for improved */
     int32_t out_channels;
     int32_t in_channels;
@@ -64,11 +66,15 @@ const char* sdr_error_string(int code);
  * :347-354, :401-403; causal_improved_sudormrf_v3.py:146-189, :71-96) and the
  * element count of parameter i.  For the causal model the caller passes
  * skipinit_gain already multiplied by the block's alpha and proj_1x1's weight
- * divided by its beta (both 1.0 in the reference's constructor, :165-174).    */
+ * divided by its beta (both 1.0 in the reference's constructor, :165-174).
+ * Original model (variant 3, sudormrf.py:211-264, :134-162): every state_dict
+ * entry in order EXCEPT the trailing ln_mask_in.{weight,bias}, which forward
+ * never reads (:264).                                                         */
 int     sdr_num_params(const sdr_config* cfg);
 int64_t sdr_param_numel(const sdr_config* cfg, int index);
 
-/* Padded length rule of pad_to_appropriate_length (improved_sudormrf.py:303-310). */
+/* Padded length rule of pad_to_appropriate_length (improved_sudormrf.py:303-310;
+ * variant 3: sudormrf.py:206-209,283-293, multiples of lcm(hop, 2^depth)).     */
 int64_t sdr_padded_length(const sdr_config* cfg, int64_t T);
 
 /* Packed weights: one flat device buffer holding every parameter plus derived
@@ -88,7 +94,8 @@ size_t sdr_workspace_bytes(const sdr_config* cfg, int B, int64_t T);
 
 /* SuDORMRF.forward (improved_sudormrf.py:283-301) /
  * GroupCommSudoRmRf.forward (groupcomm_sudormrf_v2.py:302-322) /
- * CausalSuDORMRF.forward (causal_improved_sudormrf_v3.py:191-211), optionally
+ * CausalSuDORMRF.forward (causal_improved_sudormrf_v3.py:191-211) /
+ * the original SuDORMRF.forward (sudormrf.py:266-292), optionally
  * followed by mixture_consistency.apply(..., 'uniform')
  * (mixture_consistency.py:14-36; only when in_audio_channels == 1).
  *   mixture: device [B, in_audio_channels, T] fp32 contiguous
@@ -133,8 +140,9 @@ typedef struct {
     const double* stats;   /* [samples][2] or NULL = no normalisation */
     const float*  gamma;   /* [C] */
     const float*  beta;    /* [C] */
-    const float*  prelu;   /* 1 element, or NULL = no activation */
+    const float*  prelu;   /* 1 element ([C] when prelu_per_channel), or NULL = no activation */
     double        count;   /* elements per sample the statistics were taken over */
+    int32_t       prelu_per_channel;   /* 0: nn.PReLU() (one shared slope); 1: nn.PReLU(C) (sudormrf.py:33,71) */
 } sdr_norm_in;
 
 /* nn.Conv1d(A, N, k, stride=k/2, padding=k/2, bias=False) on the zero-padded
@@ -218,6 +226,20 @@ int sdr_tac(const float* x, const float* const* params, float* o, double* stats_
  * frames [B, SA*K, L] -> out [B, SA, T] (improved_sudormrf.py:272-279,300-301). */
 int sdr_overlap_add(const float* frames, const float* mix_or_null, float* out,
                     int B, int SA, int K, int L, int64_t T, sdr_stream stream);
+
+/* ---- stages that only the original model has (sudormrf.py) ---------------- */
+
+/* Tail of the original UBlock (sudormrf.py:184-186) up to the statistics module_act needs:
+ *   x[b,c,l] <- GN_e(e)[b,c,l] + f(x[b,c,l])      in place, (sum, sumsq) of the new x into stats_out
+ * e [samples,C,L]: raw conv_1x1_exp.conv output, fe its GroupNorm (stats + weight/bias, no activation);
+ * fx: how the block input is read: NULL stats = plain tensor (first block), else module_act of the previous
+ * block (GroupNorm + per-channel PReLU) applied on load.                                                   */
+int sdr_residual_norm(const float* e, const sdr_norm_in* fe, float* x, const sdr_norm_in* fx, double* stats_out,
+                      int samples, int C, int L, sdr_stream stream);
+
+/* Masks of the original model (sudormrf.py:285-289): logits [B,S,N,L] (the (N+1)x1 Conv2d output) ->
+ * softmax over the S sources (sigmoid when S == 1) times the encoder output enc [B,N,L]; in place is allowed. */
+int sdr_softmax_gate(const float* logits, const float* enc, float* out, int B, int S, int N, int L, sdr_stream stream);
 
 /* ---- the steps either side of the forward -------- */
 

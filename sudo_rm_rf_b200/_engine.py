@@ -53,6 +53,23 @@ def state_dict_names(cfg: N.SdrConfig) -> List[str]:
             names += [p + "res_conv.weight", p + "res_conv.bias"]
         names += ["mask_net.0.weight", "mask_net.1.weight", "mask_net.1.bias", "decoder.weight", "mask_nl_class.weight"]
         return names
+    if cfg.variant == 3:       # the original model, sudormrf.py:211-252 (block :134-162); ln_mask_in (:253) is never read
+        names = ["encoder.0.weight", "encoder.0.bias", "ln.weight", "ln.bias", "l1.weight", "l1.bias"]
+        for i in range(cfg.num_blocks):
+            p = f"sm.{i}."
+            names += [p + "proj_1x1.conv.weight", p + "proj_1x1.conv.bias", p + "proj_1x1.norm.weight",
+                      p + "proj_1x1.norm.bias", p + "proj_1x1.act.weight"]
+            for d in range(cfg.upsampling_depth):
+                names += [p + f"spp_dw.{d}.conv.weight", p + f"spp_dw.{d}.conv.bias",
+                          p + f"spp_dw.{d}.norm.weight", p + f"spp_dw.{d}.norm.bias"]
+            names += [p + "conv_1x1_exp.conv.weight", p + "conv_1x1_exp.conv.bias", p + "conv_1x1_exp.norm.weight",
+                      p + "conv_1x1_exp.norm.bias", p + "final_norm.norm.weight", p + "final_norm.norm.bias",
+                      p + "final_norm.act.weight", p + "module_act.norm.weight", p + "module_act.norm.bias",
+                      p + "module_act.act.weight"]
+        if cfg.out_channels != cfg.enc_num_basis:
+            names += ["reshape_before_masks.weight", "reshape_before_masks.bias"]
+        names += ["m.weight", "m.bias", "decoder.weight", "decoder.bias"]
+        return names
     names = ["encoder.weight", "ln.gamma", "ln.beta", "bottleneck.weight", "bottleneck.bias"]
 
     def ublock(p):
@@ -77,6 +94,13 @@ def state_dict_names(cfg: N.SdrConfig) -> List[str]:
             names += ublock(f"sm.{i}.UBlock.")
     names += ["mask_net.0.weight", "mask_net.1.weight", "mask_net.1.bias", "decoder.weight"]
     return names
+
+
+def _probe_names(model):
+    """First and last parameter of the model (device / requires_grad probes)."""
+    if getattr(model, "_b200_variant", None) == 3:
+        return ("encoder.0.weight", "decoder.weight")
+    return ("encoder.weight", "decoder.weight")
 
 
 def _fetch(model, dotted: str) -> torch.Tensor:
@@ -274,7 +298,7 @@ def _check_input(model, cfg, wav: torch.Tensor) -> torch.Tensor:
             "sudo_rm_rf_b200 runs on CUDA (sm_100a) only and has no CPU path: move the model "
             "and the mixture to a B200 (`model.cuda()`, `mixture.cuda()`).")
     if torch.is_grad_enabled() and model.training and \
-            any(_fetch(model, n).requires_grad for n in ("encoder.weight", "decoder.weight")):
+            any(_fetch(model, n).requires_grad for n in _probe_names(model)):
         raise RuntimeError(
             "sudo_rm_rf_b200 implements the inference forward only (no autograd): call "
             "model.eval() and/or wrap the call in torch.no_grad().")
@@ -282,7 +306,7 @@ def _check_input(model, cfg, wav: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("empty batch or zero-length mixture")
     global _warned_detached
     if torch.is_grad_enabled() and not _warned_detached and \
-            any(_fetch(model, n).requires_grad for n in ("encoder.weight", "decoder.weight")):
+            any(_fetch(model, n).requires_grad for n in _probe_names(model)):
         _warned_detached = True
         warnings.warn("sudo_rm_rf_b200: the native forward is inference-only; the returned estimates are detached "
                       "from autograd (wrap the call in torch.no_grad() to silence this).", stacklevel=3)
@@ -365,7 +389,7 @@ def forward_host(model, host_wav: torch.Tensor, host_out: torch.Tensor = None,
     if host_wav.dim() != 3 or host_wav.is_cuda or host_wav.dtype != torch.float32 \
             or not host_wav.is_contiguous():
         raise RuntimeError("forward_host expects a contiguous fp32 CPU tensor [B, A, T]")
-    device = torch.device(device) if device is not None else _fetch(model, "encoder.weight").device
+    device = torch.device(device) if device is not None else _fetch(model, _probe_names(model)[0]).device
     if device.type != "cuda":
         raise RuntimeError("the model must live on a CUDA device")
     if device.index is None:

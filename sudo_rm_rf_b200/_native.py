@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDR_B200_LIB") or os.path.join(_HERE, "libsudormrf_b200.so")   # env override: A/B-testing kernel builds
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SdrConfig(C.Structure):
@@ -31,7 +31,7 @@ class SdrConfig(C.Structure):
 class SdrNormIn(C.Structure):
     """``sdr_norm_in``."""
     _fields_ = [("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
-                ("prelu", C.c_void_p), ("count", C.c_double)]
+                ("prelu", C.c_void_p), ("count", C.c_double), ("prelu_per_channel", C.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -90,6 +90,9 @@ _SIGNATURES = {
                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sdr_tac": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int,
                           C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sdr_residual_norm": (C.c_int, [C.c_void_p, C.POINTER(SdrNormIn), C.c_void_p, C.POINTER(SdrNormIn), C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sdr_softmax_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sdr_overlap_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int64, C.c_void_p]),
     "sdr_utterance_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -22,8 +22,8 @@ int launch_pyramid(const float*, const NormIn&, const float* const*, const float
 int launch_merge_pyramid(const float* const*, const float*, int, float*, double*, int, int, int, cudaStream_t);
 int launch_pointwise_ffma(const float*, const NormIn&, const float*, const float*, const float*, const float*, int,
                           float*, double*, int, int, int, int, int, cudaStream_t);
-int launch_encoder(const float*, const float*, float*, double*, int, int, long long, int, int, int, int, cudaStream_t);
-int launch_overlap_add(const float*, const float*, const float2*, float*, int, int, int, int, long long, cudaStream_t);
+int launch_encoder(const float*, const float*, const float*, int, float*, double*, int, int, long long, int, int, int, int, cudaStream_t);
+int launch_overlap_add(const float*, const float*, const float*, const float2*, float*, int, int, int, int, long long, cudaStream_t);
 int launch_mixture_consistency(const float*, const float*, float*, int, int, long long, int, void*, cudaStream_t);
 int launch_tac(const float*, const float* const*, float*, double*, int, int, int, int, cudaStream_t);
 int launch_tac_apply(const float*, const float*, const NormIn&, float*, int, int, int, cudaStream_t);
@@ -35,6 +35,11 @@ int launch_causal_pyramid(const float*, const float*, const float* const*, const
                           int, int, int, int, cudaStream_t);
 int launch_take_taps(const float*, float*, long long, int, int, cudaStream_t);
 int launch_scale_by_scalar(const float*, const float*, float*, long long, cudaStream_t);
+// original model (original.cu)
+int launch_residual_norm(const float*, const NormIn&, float*, const NormIn&, double*, int, int, int, cudaStream_t);
+int launch_softmax_gate(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+int launch_toeplitz_mask(const float*, const float*, float*, float*, int, int, cudaStream_t);
+int launch_grouped_decoder(const float*, float*, int, int, int, cudaStream_t);
 // pre/post steps (prepost.cu)
 int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
 int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
@@ -83,12 +88,27 @@ struct CausalBlockOff {
     size_t proj_pk, res_pk;
 };
 
+// sudormrf.py:134-162: proj_1x1 (conv, GroupNorm, PReLU(Ci)), spp_dw[d] (depthwise conv, GroupNorm), conv_1x1_exp (conv,
+// GroupNorm), final_norm (GroupNorm, PReLU(Ci)), module_act (GroupNorm, PReLU(Co)), in state_dict order
+struct OrigBlockOff {
+    size_t proj_w, proj_b, proj_g, proj_be, proj_a;
+    size_t dw_w[kMaxDepthApi], dw_b[kMaxDepthApi], dw_g[kMaxDepthApi], dw_be[kMaxDepthApi];
+    size_t exp_w, exp_b, exp_g, exp_be;
+    size_t fn_g, fn_be, fn_a;
+    size_t ma_g, ma_be, ma_a;
+    size_t proj_pk, exp_pk;
+};
+
 struct Layout {
     bool ok = false;
     int A, N, Co, Ci, U, D, K, S, G, hop;
     int cob, cib;                 // channels seen by one U-ConvBlock (Co/G, Ci/G for groupcomm)
     bool gc;
     bool causal = false;          // variant 2: CausalSuDORMRF
+    bool orig = false;            // variant 3: the original SuDORMRF (sudormrf.py)
+    std::vector<OrigBlockOff> ob;
+    size_t enc_b = 0, rs_w = 0, rs_b = 0, m_w = 0, m_b = 0, dec_b = 0;   // orig: encoder bias, reshape_before_masks, m, decoder bias
+    size_t toep_w = 0, toep_b = 0, rs_pk = 0;                            // orig, derived: [S*N][N] mask matrix + its row bias
     std::vector<CausalBlockOff> cb;
     size_t mask_nl = 0;           // causal: mask_nl_class.weight (PReLU on the masks)
     size_t enc_wc = 0;            // causal: derived [N][A][K], the encoder taps the causal mask keeps
@@ -106,7 +126,8 @@ static Layout make_layout(const sdr_config* c) {
     if (!c) return l;
     l.gc = c->variant == 1;
     l.causal = c->variant == 2;
-    if (c->variant < 0 || c->variant > 2) return l;
+    l.orig = c->variant == 3;
+    if (c->variant < 0 || c->variant > 3) return l;
     l.A = (l.gc || l.causal) ? c->in_audio_channels : 1;
     l.N = c->enc_num_basis; l.Co = c->out_channels; l.Ci = c->in_channels;
     l.U = c->num_blocks; l.D = c->upsampling_depth; l.K = c->enc_kernel_size;
@@ -118,9 +139,56 @@ static Layout make_layout(const sdr_config* c) {
     if (l.S * l.A > 16) return l;
     if (l.gc && (l.Co % l.G || l.Ci % l.G)) return l;
     l.cob = l.Co / l.G; l.cib = l.Ci / l.G;
+    if (l.orig && (l.N % 2)) return l;   // (N+1) x 1 mask conv with padding N - N/2 returns N rows only for an even N (sudormrf.py:239-242,289)
 
     size_t cur = 0;
     auto add = [&](size_t n) { size_t o = cur; l.off.push_back(o); l.numel.push_back(n); cur += (n + 3) & ~(size_t)3; return o; };
+    if (l.orig) {
+        // state_dict order of the original SuDORMRF (sudormrf.py:211-252; block :134-162) without ln_mask_in (:253, unused)
+        l.enc_w = add((size_t)l.N * l.K); l.enc_b = add(l.N);
+        l.ln_g = add(l.N); l.ln_be = add(l.N);
+        l.bn_w = add((size_t)l.Co * l.N); l.bn_b = add(l.Co);                      // l1
+        for (int i = 0; i < l.U; ++i) {
+            OrigBlockOff u;
+            u.proj_w = add((size_t)l.Ci * l.Co); u.proj_b = add(l.Ci);
+            u.proj_g = add(l.Ci); u.proj_be = add(l.Ci); u.proj_a = add(l.Ci);
+            for (int d = 0; d < l.D; ++d) {
+                u.dw_w[d] = add((size_t)l.Ci * 5); u.dw_b[d] = add(l.Ci);
+                u.dw_g[d] = add(l.Ci); u.dw_be[d] = add(l.Ci);
+            }
+            u.exp_w = add((size_t)l.Co * l.Ci); u.exp_b = add(l.Co); u.exp_g = add(l.Co); u.exp_be = add(l.Co);
+            u.fn_g = add(l.Ci); u.fn_be = add(l.Ci); u.fn_a = add(l.Ci);
+            u.ma_g = add(l.Co); u.ma_be = add(l.Co); u.ma_a = add(l.Co);
+            u.proj_pk = u.exp_pk = 0;
+            l.ob.push_back(u);
+        }
+        if (l.Co != l.N) { l.rs_w = add((size_t)l.N * l.Co); l.rs_b = add(l.N); }   // :233-236
+        l.m_w = add((size_t)l.S * (l.N + 1)); l.m_b = add(l.S);
+        l.dec_w = add((size_t)l.S * l.N * l.K); l.dec_b = add(l.S);
+        auto derived = [&](size_t n) { size_t o = cur; cur += (n + 3) & ~(size_t)3; return o; };
+        l.toep_w = derived((size_t)l.S * l.N * l.N);
+        l.toep_b = derived((size_t)l.S * l.N);
+        l.dec_wt = derived((size_t)l.S * l.K * l.S * l.N);
+        cur = (cur + 63) & ~(size_t)63;
+        auto add_pk = [&](int M, int K) -> size_t {
+            const size_t b = pointwise_mma_packed_bytes(M, K);
+            if (!b) return 0;
+            const size_t o = cur; cur += b / sizeof(float); return o;
+        };
+        l.bn_pk = add_pk(l.Co, l.N);
+        for (int i = 0; i < l.U; ++i) {
+            l.ob[i].proj_pk = add_pk(l.Ci, l.Co);
+            l.ob[i].exp_pk = add_pk(l.Co, l.Ci);
+        }
+        l.rs_pk = l.rs_w ? add_pk(l.N, l.Co) : 0;
+        l.mask_pk = add_pk(l.S * l.N, l.N);
+        l.dec_pk = add_pk(l.S * l.K, l.S * l.N);
+        l.enc_pk = 0;                                   // biased encoder + ReLU: the FFMA encoder kernel
+        l.mask_a = l.mask_w = l.mask_b = 0;
+        l.total = cur;
+        l.ok = true;
+        return l;
+    }
     if (l.causal) {
         // state_dict order of CausalSuDORMRF (causal_improved_sudormrf_v3.py:146-189; block :71-96)
         l.enc_w = add((size_t)l.N * l.A * (2 * l.K - 1));
@@ -221,7 +289,14 @@ static Layout make_layout(const sdr_config* c) {
     return l;
 }
 
+static long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; }
+
 static long long padded_len(const Layout& l, long long T) {
+    if (l.orig) {                                          // sudormrf.py:206-209,283-293: multiples of lcm(hop, 2^D), no minimum
+        const long long p2 = 1LL << l.D;
+        const long long q = (long long)l.hop * p2 / gcd_ll(l.hop, p2);
+        return T % q ? T + q - T % q : T;
+    }
     const long long q = (long long)l.hop << l.D;          // improved_sudormrf.py:244
     if (T < q) return q;
     return (T + q - 1) / q * q;
@@ -252,7 +327,7 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     p.Tp = padded_len(l, T);
     p.L = (int)(p.Tp / l.hop);
     p.samples = B * l.G;
-    p.slots = l.causal ? 1 : 1 + l.U * (l.D + 2 + (l.gc ? 1 : 0));
+    p.slots = l.causal ? 1 : 1 + l.U * (l.D + 2 + (l.gc ? 1 : 0) + (l.orig ? 2 : 0));
     p.stats_doubles = (size_t)p.slots * p.samples * 2;
     size_t cur = 0;
     auto seg = [&](size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~(size_t)255; return o; };
@@ -260,8 +335,8 @@ static Plan make_plan(const Layout& l, int B, long long T) {
     p.o_stats = seg(p.stats_doubles * sizeof(double));
     p.o_e = seg(BL * l.N);
     p.o_x = seg(BL * l.Co);
-    p.o_xt = l.gc ? seg(BL * l.Co) : 0;
-    p.o_o = l.gc ? seg(BL * l.Co) : 0;
+    p.o_xt = (l.gc || l.orig) ? seg(BL * l.Co) : 0;                       // orig: conv_1x1_exp output
+    p.o_o = l.gc ? seg(BL * l.Co) : ((l.orig && l.rs_w) ? seg(BL * l.N) : 0);   // orig: reshape_before_masks output
     p.o_y = seg(BL * l.Ci);
     for (int d = 0; d < kMaxDepthApi; ++d) p.o_z[d] = (d < l.D && !(l.causal && d > 0)) ? seg((BL * l.Ci) >> d) : 0;
     p.pyramid = !l.causal && pyramid_eligible(l.D, l.cib, p.L);
@@ -291,7 +366,7 @@ static int forward_causal(const Layout& l, const float* pk, const float* mixture
     // encoder (:194): 2k-1 taps of which the causal mask keeps the first k, i.e. the improved model's encoder reading
     // one hop further into the past (left padding 2 * hop)
     if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
-    else SDR_TRY(launch_encoder(mixture, pk + l.enc_wc, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
+    else SDR_TRY(launch_encoder(mixture, pk + l.enc_wc, nullptr, 0, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
     SDR_TRY(pointwise(e, none, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
                       x, nullptr, B, l.Co, l.N, L, 0, st));                                      // :199
     for (int i = 0; i < l.U; ++i) {
@@ -315,7 +390,102 @@ static int forward_causal(const Layout& l, const float* pk, const float* mixture
                           frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
     }
     const float* mix = apply_mc ? mixture : nullptr;
-    SDR_TRY(launch_overlap_add(frames, mix, rescale, out, B, l.S * l.A, l.K, L, T, st));
+    SDR_TRY(launch_overlap_add(frames, mix, nullptr, rescale, out, B, l.S * l.A, l.K, L, T, st));
+    return SDR_OK;
+}
+
+// The original SuDORMRF.forward (sudormrf.py:266-292; UBlock.forward :164-186).
+static int forward_original(const Layout& l, const float* pk, const float* mixture, float* out,
+                            int B, long long T, int apply_mc, char* ws, cudaStream_t st, const float2* rescale) {
+    const Plan p = make_plan(l, B, T);
+    const int L = p.L, D = l.D, Co = l.Co, Ci = l.Ci, N = l.N, S = l.S;
+    double* stats = reinterpret_cast<double*>(ws + p.o_stats);
+    float* e = reinterpret_cast<float*>(ws + p.o_e);
+    float* x = reinterpret_cast<float*>(ws + p.o_x);
+    float* ex = reinterpret_cast<float*>(ws + p.o_xt);
+    float* y = reinterpret_cast<float*>(ws + p.o_y);
+    float* z[kMaxDepthApi];
+    for (int d = 0; d < D; ++d) z[d] = reinterpret_cast<float*>(ws + p.o_z[d]);
+    float* masked = reinterpret_cast<float*>(ws + p.o_masked);
+    float* frames = reinterpret_cast<float*>(ws + p.o_frames);
+    auto slot = [&](int s) { return stats + (size_t)s * p.samples * 2; };
+    const NormIn none{nullptr, nullptr, nullptr, nullptr, 1.0, 0};
+    if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
+
+    // front end (:268-276): biased encoder + ReLU (+stats), ln folded into l1's operand load
+    SDR_TRY(launch_encoder(mixture, pk + l.enc_w, pk + l.enc_b, 1, e, slot(0), B, 1, T, N, l.K, L, l.hop, st));
+    {
+        NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)N * L, 0};
+        SDR_TRY(pointwise(e, ln, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
+                          x, nullptr, B, Co, N, L, 0, st));
+    }
+    // x holds u_i = GN(conv_1x1_exp(..)) + block input (raw); the block output PReLU_c(GN_ma(u_i)) is applied by its readers
+    NormIn xin = none;
+    for (int i = 0; i < l.U; ++i) {
+        const int s0 = 1 + i * (D + 4);
+        const OrigBlockOff& u = l.ob[i];
+        SDR_TRY(pointwise(x, xin, pk + u.proj_w, u.proj_pk ? pk + u.proj_pk : nullptr, pk + u.proj_b, nullptr, nullptr, 0,
+                          y, slot(s0), B, Ci, Co, L, 0, st));                                        // :171
+        const NormIn n0{slot(s0), pk + u.proj_g, pk + u.proj_be, pk + u.proj_a, (double)Ci * L, 1};
+        bool pyr_done = false;
+        if (p.pyramid) {
+            const float *pw[kMaxDepthApi], *pb[kMaxDepthApi], *pg[kMaxDepthApi], *pbe[kMaxDepthApi];
+            const float* zc[kMaxDepthApi];
+            for (int d = 0; d < D; ++d) {
+                pw[d] = pk + u.dw_w[d]; pb[d] = pk + u.dw_b[d]; pg[d] = pk + u.dw_g[d]; pbe[d] = pk + u.dw_be[d];
+                zc[d] = z[d];
+            }
+            int rc = launch_pyramid(y, n0, pw, pb, pg, pbe, z, slot(s0 + 1), reinterpret_cast<double*>(ws + p.o_rowstats),
+                                    reinterpret_cast<float*>(ws + p.o_table), D, B, Ci, L, st);
+            if (rc == SDR_OK) {
+                SDR_TRY(launch_merge_pyramid(zc, reinterpret_cast<const float*>(ws + p.o_table), D, y, slot(s0 + D + 1),
+                                             B, Ci, L, st));
+                pyr_done = true;
+            } else if (rc != SDR_ERR_UNSUPPORTED) {
+                return rc;
+            }
+        }
+        if (!pyr_done) {                                                                             // :172-182
+            SDR_TRY(launch_depthwise(y, n0, pk + u.dw_w[0], pk + u.dw_b[0], z[0], slot(s0 + 1), B, Ci, L, 1, st));
+            for (int d = 1; d < D; ++d) {
+                NormIn nd{slot(s0 + d), pk + u.dw_g[d - 1], pk + u.dw_be[d - 1], nullptr, (double)Ci * (L >> (d - 1)), 0};
+                SDR_TRY(launch_depthwise(z[d - 1], nd, pk + u.dw_w[d], pk + u.dw_b[d], z[d], slot(s0 + 1 + d),
+                                         B, Ci, L >> (d - 1), 2, st));
+            }
+            NormIn nm[kMaxDepthApi];
+            const float* zc[kMaxDepthApi];
+            for (int d = 0; d < D; ++d) {
+                nm[d] = NormIn{slot(s0 + 1 + d), pk + u.dw_g[d], pk + u.dw_be[d], nullptr, (double)Ci * (L >> d), 0};
+                zc[d] = z[d];
+            }
+            SDR_TRY(launch_merge(zc, nm, D, y, slot(s0 + D + 1), B, Ci, L, st));                      // m reuses y's storage
+        }
+        {                                                                                            // :184 conv_1x1_exp.conv
+            NormIn nf{slot(s0 + D + 1), pk + u.fn_g, pk + u.fn_be, pk + u.fn_a, (double)Ci * L, 1};
+            SDR_TRY(pointwise(y, nf, pk + u.exp_w, u.exp_pk ? pk + u.exp_pk : nullptr, pk + u.exp_b, nullptr, nullptr, 0,
+                              ex, slot(s0 + D + 2), B, Co, Ci, L, 0, st));
+        }
+        {                                                                                            // :184 .norm, :186 + x
+            NormIn ne{slot(s0 + D + 2), pk + u.exp_g, pk + u.exp_be, nullptr, (double)Co * L, 0};
+            SDR_TRY(launch_residual_norm(ex, ne, x, xin, slot(s0 + D + 3), B, Co, L, st));
+        }
+        xin = NormIn{slot(s0 + D + 3), pk + u.ma_g, pk + u.ma_be, pk + u.ma_a, (double)Co * L, 1};  // :186 module_act
+    }
+    const float* mask_in = x;                              // input of the mask convolution and how to read it
+    NormIn mnin = xin;
+    if (l.rs_w) {                                                                                     // :279-281
+        float* r = reinterpret_cast<float*>(ws + p.o_o);
+        SDR_TRY(pointwise(x, xin, pk + l.rs_w, l.rs_pk ? pk + l.rs_pk : nullptr, pk + l.rs_b, nullptr, nullptr, 0,
+                          r, nullptr, B, N, Co, L, 0, st));
+        mask_in = r; mnin = none;
+    }
+    SDR_TRY(pointwise(mask_in, mnin, pk + l.toep_w, l.mask_pk ? pk + l.mask_pk : nullptr, pk + l.toep_b, nullptr, nullptr, 0,
+                      masked, nullptr, B, S * N, N, L, 0, st));                                       // :284
+    SDR_TRY(launch_softmax_gate(masked, e, masked, B, S, N, L, st));                                  // :285-289
+    SDR_TRY(pointwise(masked, none, pk + l.dec_wt, l.dec_pk ? pk + l.dec_pk : nullptr, nullptr, nullptr, nullptr, 0,
+                      frames, nullptr, B, S * l.K, S * N, L, 0, st));                                 // :291
+    const float* mix = apply_mc ? mixture : nullptr;
+    SDR_TRY(launch_overlap_add(frames, mix, pk + l.dec_b, rescale, out, B, S, l.K, L, T, st));
     return SDR_OK;
 }
 
@@ -326,6 +496,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     // [B, 1, T] mixture: it is only defined for mono models; refuse instead of silently skipping the projection
     if (apply_mc && l.A != 1) return SDR_ERR_UNSUPPORTED;
     if (l.causal) return forward_causal(l, pk, mixture, out, B, T, apply_mc, ws, st, rescale);
+    if (l.orig) return forward_original(l, pk, mixture, out, B, T, apply_mc, ws, st, rescale);
     const Plan p = make_plan(l, B, T);
     const int L = p.L, D = l.D;
     double* stats = reinterpret_cast<double*>(ws + p.o_stats);
@@ -345,7 +516,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
 
     // front end: encoder (+stats), ln folded into the bottleneck's operand load
     if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
-    else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
+    else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, nullptr, 0, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
     {
         NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)l.N * L};
         SDR_TRY(pointwise(e, ln, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
@@ -439,7 +610,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     SDR_TRY(pointwise(masked, none, pk + l.dec_wt, l.dec_pk ? pk + l.dec_pk : nullptr, nullptr, nullptr, nullptr, 0,
                       frames, nullptr, B, l.S * l.A * l.K, l.S * l.A * l.N, L, 0, st));
     const float* mix = apply_mc ? mixture : nullptr;
-    SDR_TRY(launch_overlap_add(frames, mix, rescale, out, B, l.S * l.A, l.K, L, T, st));
+    SDR_TRY(launch_overlap_add(frames, mix, nullptr, rescale, out, B, l.S * l.A, l.K, L, T, st));
     return SDR_OK;
 }
 
@@ -505,6 +676,20 @@ int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_pa
         if (cudaMemcpyAsync(pk + l.off[i], params[i], l.numel[i] * sizeof(float),
                             cudaMemcpyDeviceToDevice, st) != cudaSuccess) return SDR_ERR_CUDA;
     }
+    if (l.orig) {
+        SDR_TRY(launch_toeplitz_mask(pk + l.m_w, pk + l.m_b, pk + l.toep_w, pk + l.toep_b, l.S, l.N, st));
+        SDR_TRY(launch_grouped_decoder(pk + l.dec_w, pk + l.dec_wt, l.S, l.N, l.K, st));
+        if (l.bn_pk) SDR_TRY(pack_pointwise_mma(pk + l.bn_w, l.Co, l.N, pk + l.bn_pk, st));
+        for (int i = 0; i < l.U; ++i) {
+            const OrigBlockOff& u = l.ob[i];
+            if (u.proj_pk) SDR_TRY(pack_pointwise_mma(pk + u.proj_w, l.Ci, l.Co, pk + u.proj_pk, st));
+            if (u.exp_pk) SDR_TRY(pack_pointwise_mma(pk + u.exp_w, l.Co, l.Ci, pk + u.exp_pk, st));
+        }
+        if (l.rs_pk) SDR_TRY(pack_pointwise_mma(pk + l.rs_w, l.N, l.Co, pk + l.rs_pk, st));
+        if (l.mask_pk) SDR_TRY(pack_pointwise_mma(pk + l.toep_w, l.S * l.N, l.N, pk + l.mask_pk, st));
+        if (l.dec_pk) SDR_TRY(pack_pointwise_mma(pk + l.dec_wt, l.S * l.K, l.S * l.N, pk + l.dec_pk, st));
+        return SDR_OK;
+    }
     const int C = l.S * l.A * l.N, SAK = l.S * l.A * l.K;
     const long long n = (long long)C * SAK;
     transpose_decoder_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pk + l.dec_w, pk + l.dec_wt, C, SAK);
@@ -551,6 +736,9 @@ static int check_forward_args(const Layout& l, int B, int64_t T) {
     }
     if (padded_len(l, T) / l.hop > 0x3fffffffLL) return SDR_ERR_UNSUPPORTED;
     if (l.causal && !causal_pyramid_eligible(l.D, (int)(padded_len(l, T) / l.hop))) return SDR_ERR_UNSUPPORTED;
+    // original model: lcm(hop, 2^D) padding makes L a multiple of 2^D / gcd(hop, 2^D); the D - 1 stride-2 levels need
+    // exact halvings (the reference's up-sample + add fails otherwise, sudormrf.py:180-182)
+    if (l.orig && ((padded_len(l, T) / l.hop) % (1LL << (l.D - 1))) != 0) return SDR_ERR_UNSUPPORTED;
     return SDR_OK;
 }
 
@@ -572,6 +760,11 @@ static int launch_count(const Layout& l, long long T) {
     // encoder + bottleneck + U * (proj + levels + merge + res [+ tac (+ tac_apply unless it is folded into proj)])
     // + mask + decoder GEMM + overlap-add; levels = pyramid + solve when the one-pass path takes the shape, else D launches
     if (l.causal) return 2 + 3 * l.U + 3;      // encoder, bottleneck, U x (proj, depthwise pyramid, res), mask, decoder, overlap-add
+    if (l.orig) {                              // encoder, l1, U x (proj, levels, merge, exp, residual-norm), [reshape], mask GEMM, softmax-gate, decoder, overlap-add
+        const int Lo = (int)(padded_len(l, T) / l.hop);
+        const int lev = pyramid_eligible(l.D, l.Ci, Lo) ? 2 : l.D;
+        return 2 + l.U * (lev + 4) + (l.rs_w ? 1 : 0) + 4;
+    }
     const bool folded = l.gc && l.U > 0 && !l.ub[0].proj_pk && l.cob <= 64 && l.cib <= 64 && l.D >= 2;   // L % 4 == 0 then
     const int L = (int)(padded_len(l, T) / l.hop);
     const int levels = pyramid_eligible(l.D, l.cib, L) ? 2 : l.D;
@@ -627,7 +820,7 @@ int sdr_encoder(const float* wav, const float* weight, float* enc, double* stats
                 int B, int A, int64_t T, int N, int K, int L, sdr_stream stream) {
     if (!wav || !weight || !enc || !stats) return SDR_ERR_BAD_ARGUMENT;
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
-    return launch_encoder(wav, weight, enc, stats, B, A, T, N, K, L, K / 2, static_cast<cudaStream_t>(stream));
+    return launch_encoder(wav, weight, nullptr, 0, enc, stats, B, A, T, N, K, L, K / 2, static_cast<cudaStream_t>(stream));
 }
 
 size_t sdr_encoder_mma_packed_bytes(int N, int A, int K) { return encoder_mma_packed_bytes(N, A, K); }
@@ -726,7 +919,17 @@ int sdr_overlap_add(const float* frames, const float* mix_or_null, float* out, i
                     int L, int64_t T, sdr_stream stream) {
     if (!frames || !out) return SDR_ERR_BAD_ARGUMENT;
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
-    return launch_overlap_add(frames, mix_or_null, nullptr, out, B, SA, K, L, T, static_cast<cudaStream_t>(stream));
+    return launch_overlap_add(frames, mix_or_null, nullptr, nullptr, out, B, SA, K, L, T, static_cast<cudaStream_t>(stream));
+}
+
+int sdr_residual_norm(const float* e, const sdr_norm_in* fe, float* x, const sdr_norm_in* fx, double* stats_out,
+                      int samples, int C, int L, sdr_stream stream) {
+    return launch_residual_norm(e, make_norm(fe), x, make_norm(fx), stats_out, samples, C, L,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int sdr_softmax_gate(const float* logits, const float* enc, float* out, int B, int S, int N, int L, sdr_stream stream) {
+    return launch_softmax_gate(logits, enc, out, B, S, N, L, static_cast<cudaStream_t>(stream));
 }
 
 // ---- steps either side of the forward ----

@@ -18,11 +18,15 @@ struct NormIn {
     const float* beta;
     const float* prelu;
     double count;
+    int prelu_pc;          // 1: one PReLU slope per channel (the original model, sudormrf.py:33,71); 0: one shared slope
 };
 
 __host__ inline NormIn make_norm(const sdr_norm_in* n) {
-    NormIn r{nullptr, nullptr, nullptr, nullptr, 1.0};
-    if (n) { r.stats = n->stats; r.gamma = n->gamma; r.beta = n->beta; r.prelu = n->prelu; r.count = n->count; }
+    NormIn r{nullptr, nullptr, nullptr, nullptr, 1.0, 0};
+    if (n) {
+        r.stats = n->stats; r.gamma = n->gamma; r.beta = n->beta; r.prelu = n->prelu; r.count = n->count;
+        r.prelu_pc = n->prelu_per_channel != 0;
+    }
     return r;
 }
 
@@ -58,7 +62,7 @@ __device__ __forceinline__ ChanNorm chan_norm(const NormIn& n, const SampleNorm&
     r.a = 1.f; r.b = 0.f;
     if (n.stats) { r.a = __ldg(n.gamma + c) * s.rstd; r.b = __ldg(n.beta + c); }
     r.act = n.prelu != nullptr;
-    r.slope = r.act ? __ldg(n.prelu) : 1.f;
+    r.slope = r.act ? __ldg(n.prelu + (n.prelu_pc ? c : 0)) : 1.f;
     return r;
 }
 

@@ -5,6 +5,8 @@
 //   pad_to_appropriate_length   improved_sudormrf.py:303-314 (zeros to Tp; folded into the
 //                               load predicate here: no padded copy is ever materialised)
 //   encoder                     improved_sudormrf.py:247-251,286  Conv1d(A,N,K,stride=K/2,pad=K/2)
+//                               (original model, sudormrf.py:212-218,269: the same Conv1d with a bias, then ReLU;
+//                                its ConvTranspose1d decoder, :245-252, has one bias per source)
 //   decoder                     improved_sudormrf.py:272-279,300  ConvTranspose1d(...,stride=K/2,
 //                               padding=K/2, output_padding=K/2-1)  -> length hop*L
 //   remove_trailing_zeros       improved_sudormrf.py:316-318      crop to T
@@ -23,9 +25,9 @@ constexpr int kEncThreads = 128;
 constexpr int kEncNB = 64;
 
 __global__ void __launch_bounds__(kEncThreads)
-encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight,
+encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight, const float* __restrict__ bias,
                float* __restrict__ enc, double* __restrict__ stats,
-               int A, long long T, int N, int K, int L, int t_tiles, int pad) {
+               int A, long long T, int N, int K, int L, int t_tiles, int pad, int relu) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_red[64];
     const int hop = K / 2;
@@ -67,11 +69,13 @@ encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight,
         }
         (void)AK;
         if (t < L) {
-            const float o[4] = {a0, a1, a2, a3};
+            float o[4] = {a0, a1, a2, a3};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int n = n0 + nn + e;
                 if (n < N) {
+                    if (bias) o[e] += __ldg(bias + n);
+                    if (relu) o[e] = fmaxf(o[e], 0.f);
                     enc[((size_t)b * N + n) * L + t] = o[e];
                     st_s += o[e]; st_q = fmaf(o[e], o[e], st_q);
                 }
@@ -81,7 +85,7 @@ encoder_kernel(const float* __restrict__ wav, const float* __restrict__ weight,
     if (stats) block_stats_atomic(st_s, st_q, stats, b, s_red);
 }
 
-int launch_encoder(const float* wav, const float* weight, float* enc, double* stats,
+int launch_encoder(const float* wav, const float* weight, const float* bias, int relu, float* enc, double* stats,
                    int B, int A, long long T, int N, int K, int L, int pad, cudaStream_t st) {
     if (B <= 0 || A <= 0 || T <= 0 || N <= 0 || K < 3 || L <= 0) return SDR_ERR_BAD_ARGUMENT;
     const int hop = K / 2;
@@ -96,7 +100,7 @@ int launch_encoder(const float* wav, const float* weight, float* enc, double* st
     const long long gx = (long long)t_tiles * B;
     if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)gx, (unsigned)((N + kEncNB - 1) / kEncNB));
-    encoder_kernel<<<grid, kEncThreads, smem, st>>>(wav, weight, enc, stats, A, T, N, K, L, t_tiles, pad);
+    encoder_kernel<<<grid, kEncThreads, smem, st>>>(wav, weight, bias, enc, stats, A, T, N, K, L, t_tiles, pad, relu);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
@@ -108,7 +112,7 @@ int launch_encoder(const float* wav, const float* weight, float* enc, double* st
 constexpr int kMaxSrc = 16;
 
 __global__ void __launch_bounds__(256)
-overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ mix,
+overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ mix, const float* __restrict__ bias,
                    const float2* __restrict__ rescale, float* __restrict__ out, int SA, int K, int L, long long T) {
     const int hop = K / 2;
     const long long tau = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,6 +133,7 @@ overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ m
             const int j = (int)(tau + hop - hop * t);
             acc += __ldg(frames + ((size_t)b * SA * K + (size_t)s * K + j) * L + t);
         }
+        if (bias) acc += __ldg(bias + s);            // decoder bias of the original model (one per source)
         if (rescale) acc = __fadd_rn(__fmul_rn(acc, rs.y), rs.x);
         est[s] = acc;
         sum += acc;
@@ -138,12 +143,12 @@ overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ m
     for (int s = 0; s < SA; ++s) out[((size_t)b * SA + s) * T + tau] = est[s] + corr;
 }
 
-int launch_overlap_add(const float* frames, const float* mix, const float2* rescale, float* out, int B, int SA,
-                       int K, int L, long long T, cudaStream_t st) {
+int launch_overlap_add(const float* frames, const float* mix, const float* bias, const float2* rescale, float* out,
+                       int B, int SA, int K, int L, long long T, cudaStream_t st) {
     if (B <= 0 || SA <= 0 || K < 3 || L <= 0 || T <= 0) return SDR_ERR_BAD_ARGUMENT;
     if (SA > kMaxSrc || B > 65535) return SDR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)((T + 255) / 256), (unsigned)B);
-    overlap_add_kernel<<<grid, 256, 0, st>>>(frames, mix, rescale, out, SA, K, L, T);
+    overlap_add_kernel<<<grid, 256, 0, st>>>(frames, mix, bias, rescale, out, SA, K, L, T);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

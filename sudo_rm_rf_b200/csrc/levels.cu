@@ -456,7 +456,7 @@ int launch_depthwise(const float* x, const NormIn& nin, const float* w5, const f
     const int Lout = (Lin + 4 - 5) / stride + 1;
     const bool vec = (Lout % 4 == 0) && (stride == 1 || Lin == 2 * Lout) &&
                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0);
-    if (vec && (Lout % 8 == 0)) {
+    if (vec && (Lout % 8 == 0) && !nin.prelu_pc) {   // (per-channel PReLU slopes, the original model: dw5_vec_kernel reads them per channel)
         const long long items = (long long)C * (Lout / 8);
         const int per_cta = kDw8Threads * kDw8Items;
         const int chunks = (int)((items + per_cta - 1) / per_cta);

@@ -370,7 +370,7 @@ int launch_pointwise_ffma(const float* x, const NormIn& nin, const float* W, con
     if (residual) al |= reinterpret_cast<uintptr_t>(residual);
     if (gate) al |= reinterpret_cast<uintptr_t>(gate);
     const bool vec = (L % 4 == 0) && (al % 16 == 0);
-    if (vec && K <= kSmMaxK && M <= 64) {                 // streaming small-channel kernel
+    if (vec && K <= kSmMaxK && M <= 64 && !nin.prelu_pc) {   // streaming small-channel kernel (one shared PReLU slope)
         const int threads = small_block_threads(L / 4);
         const int chunks = (L / 4 + threads - 1) / threads;
         const long long gx = (long long)chunks * samples;

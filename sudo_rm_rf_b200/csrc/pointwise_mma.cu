@@ -348,11 +348,12 @@ __device__ __forceinline__ TileCoord decode_tile(const MmaArgs& a, int tile, int
 // producer + 8 specialised copies of the store loop) against a 32 KB L1.5 instruction cache, and the
 // per-chunk timeline showed the epilogue warps at IPC ~0.1 (instruction fetch stalls).
 //   WINDOW: encoder mode (strided waveform windows as the A operand)
-//   ACT:    PReLU in the operand transform
+//   ACT:    PReLU in the operand transform: 0 none, 1 one shared slope (nn.PReLU()), 2 one slope per input
+//           channel (nn.PReLU(C) of the original model, sudormrf.py:33,71; shared -> shared transform loop only)
 //   MODE:   epilogue 0 = bias only, 1 = + residual (may alias y), 2 = ReLU * gate,
 //           3 = in-place skip connection (y == residual): y += acc + bias as a bulk reduce-add in L2
 //   STATS:  accumulate (sum, sumsq) of the output
-template <bool WINDOW, bool ACT, int MODE, bool STATS>
+template <bool WINDOW, int ACT, int MODE, bool STATS>
 __global__ void __launch_bounds__(SDR_MMA_THREADS(MODE), 1)
 pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      // tmap: MODE 3 in-place output
               const __grid_constant__ CUtensorMap wmap,                       // wmap: packed weights as [rows][128 B]
@@ -416,9 +417,11 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
         const int pw = warp - kProdWarp0;          // k-group (8 channels) of this warp
         const int p4 = lane * 4;                   // first of this lane's 4 positions in the tile
         const bool has_norm = a.nin.stats != nullptr;
-        const float slope = ACT ? __ldg(a.nin.prelu) : 1.f;
+        const float slope = ACT == 1 ? __ldg(a.nin.prelu) : 1.f;
         const bool slope_le1 = slope <= 1.f;
-        float2* const my_tab = s_ab + pw * 64;     // this warp's [2][8] (scale, shift) table (lane e < 8)
+        float2* const my_tab = s_ab + pw * 64;     // this warp's [2][8] (scale, shift) table (lane e < 8); ACT == 2: the
+                                                   // channels' PReLU slopes in entries [16, 32) of the same 64-entry slice
+        static_assert(!(WINDOW && ACT != 0), "the encoder's window operand has no activation");
         const double inv_count = 1.0 / a.nin.count;
         const size_t Ls = (size_t)a.L;
         // byte offset of (channel row e = 0, this lane's positions) inside an A half tile
@@ -452,9 +455,12 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                 return ldg4(a.x + ((size_t)c.tc.sample * a.K + (size_t)c.kb * kBlockK + pw * 8 + e) * Ls + l);
             }
         };
-        struct Aux { float g, b; double s0, s1; };
+        struct Aux { float g, b; double s0, s1; float sl; };
         auto load_aux = [&](const Cur& c) -> Aux {   // lane e: gamma/beta of channel e of this warp's k-group
-            Aux x{1.f, 0.f, 0.0, 1.0};
+            Aux x{1.f, 0.f, 0.0, 1.0, 1.f};
+            if constexpr (ACT == 2) {
+                if (c.tile < a.num_tiles) x.sl = __ldg(a.nin.prelu + c.kb * kBlockK + pw * 8 + (lane & 7));
+            }
             if (has_norm && c.tile < a.num_tiles) {
                 const int k = c.kb * kBlockK + pw * 8 + (lane & 7);
                 x.g = __ldg(a.nin.gamma + k);
@@ -515,7 +521,10 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                             aa = aux.g * rstd;
                             bb = aux.b - mean * aa;
                         }
-                        if (lane < 8) my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
+                        if (lane < 8) {
+                            my_tab[(it & 1) * 8 + lane] = make_float2(aa, bb);
+                            if constexpr (ACT == 2) my_tab[16 + (it & 1) * 8 + lane] = make_float2(aux.sl, 0.f);
+                        }
                         aux = load_aux(n);
                     }
                     __syncwarp();                      // table visible to the warp (reuse is ordered by the next __syncwarp)
@@ -523,6 +532,11 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                     float2 abv[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) abv[e] = tab[e];
+                    float slv[ACT == 2 ? 8 : 1];
+                    if constexpr (ACT == 2) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) slv[e] = tab[16 + e].x;
+                    }
                     if (pw == 0 && lane == 0) SDR_TR(0, it, 0);
                     mbar_wait(&rfull_bar[rs], rphase);                          // raw tile landed
                     if (pw == 0 && lane == 0) SDR_TR(0, it, 1);
@@ -542,12 +556,16 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                         const float2 ab = abv[e];
                         float y[4] = {fmaf(v[e].x, ab.x, ab.y), fmaf(v[e].y, ab.x, ab.y),
                                       fmaf(v[e].z, ab.x, ab.y), fmaf(v[e].w, ab.x, ab.y)};
-                        if (ACT) {                     // PReLU in 2 ops: max(y, s*y) for s <= 1, min otherwise
+                        if constexpr (ACT == 1) {      // PReLU in 2 ops: max(y, s*y) for s <= 1, min otherwise
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const float t = y[u] * slope;
                                 y[u] = slope_le1 ? fmaxf(y[u], t) : fminf(y[u], t);
                             }
+                        } else if constexpr (ACT == 2) {   // this channel's own slope (either side of 1, either sign)
+                            const float sl = slv[ACT == 2 ? e : 0];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) y[u] = y[u] >= 0.f ? y[u] : y[u] * sl;
                         }
                         uint32_t hb[4];
 #pragma unroll
@@ -1227,7 +1245,8 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     if (pos_tiles > 0x3fffffffLL || tiles > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
     a.pos_tiles = (int)pos_tiles;
     a.num_tiles = (int)tiles;
-    const bool act = nin.prelu != nullptr;
+    const int act = nin.prelu ? (nin.prelu_pc ? 2 : 1) : 0;
+    if (act == 2 && !SDR_MMA_RAW_TMA) return SDR_ERR_UNSUPPORTED;     // per-channel slopes exist in the shared -> shared transform loop only
     // in-place skip connection (every U-ConvBlock's res_conv): the residual add happens in L2 (bulk reduce-add)
     const bool inplace = SDR_MMA_BULK && residual == y && (reinterpret_cast<uintptr_t>(y) % 16) == 0;
     const int mode = epilogue == 1 ? 2 : (residual ? (inplace ? 3 : 1) : 0);
@@ -1239,14 +1258,15 @@ int launch_pointwise_mma(const float* x, const NormIn& nin, const void* wpk, con
     if (int rc = make_act_map(&xmap, x, samples, K, L)) return rc;
 #define SDR_MMA_CASE(A, MD, ST)                                                                                   \
     if (act == A && mode == MD && stats == ST) return launch_pairs(pw_mma_kernel<false, A, MD, ST>, a, ymap, wmap, xmap, st);
-    SDR_MMA_CASE(false, 0, false) SDR_MMA_CASE(false, 0, true)
-    SDR_MMA_CASE(true, 0, false)  SDR_MMA_CASE(true, 0, true)
-    SDR_MMA_CASE(false, 1, false) SDR_MMA_CASE(false, 1, true)
-    SDR_MMA_CASE(true, 1, false)  SDR_MMA_CASE(true, 1, true)
-    SDR_MMA_CASE(false, 2, false) SDR_MMA_CASE(false, 2, true)
-    SDR_MMA_CASE(true, 2, false)  SDR_MMA_CASE(true, 2, true)
-    SDR_MMA_CASE(false, 3, false) SDR_MMA_CASE(false, 3, true)
-    SDR_MMA_CASE(true, 3, false)  SDR_MMA_CASE(true, 3, true)
+    SDR_MMA_CASE(0, 0, false) SDR_MMA_CASE(0, 0, true)
+    SDR_MMA_CASE(1, 0, false) SDR_MMA_CASE(1, 0, true)
+    SDR_MMA_CASE(0, 1, false) SDR_MMA_CASE(0, 1, true)
+    SDR_MMA_CASE(1, 1, false) SDR_MMA_CASE(1, 1, true)
+    SDR_MMA_CASE(0, 2, false) SDR_MMA_CASE(0, 2, true)
+    SDR_MMA_CASE(1, 2, false) SDR_MMA_CASE(1, 2, true)
+    SDR_MMA_CASE(0, 3, false) SDR_MMA_CASE(0, 3, true)
+    SDR_MMA_CASE(1, 3, false) SDR_MMA_CASE(1, 3, true)
+    SDR_MMA_CASE(2, 0, false) SDR_MMA_CASE(2, 0, true)      // the original model: proj_1x1 / conv_1x1_exp / mask front
 #undef SDR_MMA_CASE
     return SDR_ERR_UNSUPPORTED;
 }
@@ -1294,8 +1314,8 @@ int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* st
     if (int rc = make_weight_map(&wmap, wpk, encoder_mma_packed_bytes(N, A, Kk), a.tile_n)) return rc;
     CUtensorMap xmap;
     memset(&xmap, 0, sizeof(xmap));               // window mode gathers the waveform itself
-    if (stats) return launch_pairs(pw_mma_kernel<true, false, 0, true>, a, ymap, wmap, xmap, st);
-    return launch_pairs(pw_mma_kernel<true, false, 0, false>, a, ymap, wmap, xmap, st);
+    if (stats) return launch_pairs(pw_mma_kernel<true, 0, 0, true>, a, ymap, wmap, xmap, st);
+    return launch_pairs(pw_mma_kernel<true, 0, 0, false>, a, ymap, wmap, xmap, st);
 }
 
 }  // namespace sdr

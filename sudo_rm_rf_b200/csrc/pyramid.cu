@@ -133,13 +133,15 @@ __device__ __forceinline__ void pyr_bulk_g2s(void* dst, const void* src, uint32_
 #ifndef SDR_PYR_MINB
 #define SDR_PYR_MINB 6                  // resident CTAs per SM the <= 256-thread instantiation is compiled for (A/B on the B200: 4 -> 177 us, 5 -> 175, 6 -> 165 at cfg 2)
 #endif
-template <int D, int MAXT, int MINB>
+// PC: one PReLU slope per channel (the original model's nn.PReLU(C), sudormrf.py:33): a row is one channel, so the
+// slope simply travels with the row's other parameters; the shared-slope instantiations are unchanged.
+template <int D, int MAXT, int MINB, bool PC>
 __global__ void __launch_bounds__(MAXT, MINB)
 dw_pyramid_kernel(const PyrArgs a) {
     static_assert(D >= 4 && D <= 6, "register pyramid: levels 0..3 by lane chunks, 4 per lane, 5 per lane pair");
     constexpr int S = PyrGeom<D>::kStep, ML = PyrGeom<D>::kLeft;
     extern __shared__ __align__(16) float pyr_smem[];       // [2][L + 8]: raw rows of y with 4 floats of slack on either side
-    __shared__ float s_par[2][5 * D + 3];                   // taps of every level, bias_0, gamma_y, beta_y (one row ahead)
+    __shared__ float s_par[2][5 * D + 3 + (PC ? 1 : 0)];    // taps of every level, bias_0, gamma_y, beta_y (one row ahead) [, slope]
     __shared__ float s_part[2][32][2 * D];
     __shared__ __align__(8) uint64_t s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,16 +151,17 @@ dw_pyramid_kernel(const PyrArgs a) {
     const int samples = a.rows / a.C;
     const uint32_t row_bytes = (uint32_t)L * sizeof(float);
     const bool act = a.nin.prelu != nullptr;
-    const float slope = act ? __ldg(a.nin.prelu) : 1.f;
-    const bool sle1 = slope <= 1.f;
+    float slope = (act && !PC) ? __ldg(a.nin.prelu) : 1.f;
+    bool sle1 = slope <= 1.f;
 
     auto stage_params = [&](int row, int slot) {
-        for (int i = tid; i < 5 * D + 3; i += blockDim.x) {
+        for (int i = tid; i < 5 * D + 3 + (PC ? 1 : 0); i += blockDim.x) {
             const int c = row % a.C;
             const float* src;
             if (i < 5 * D) src = a.w[i / 5] + c * 5 + (i % 5);
             else if (i == 5 * D) src = a.bias0 + c;
             else if (i == 5 * D + 1) src = a.nin.stats ? a.nin.gamma + c : a.bias0 + c;
+            else if (PC && i == 5 * D + 3) src = act ? a.nin.prelu + c : a.bias0 + c;
             else src = a.nin.stats ? a.nin.beta + c : a.bias0 + c;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pyr_smem_u32(&s_par[slot][i])), "l"(src) : "memory");
         }
@@ -206,6 +209,7 @@ dw_pyramid_kernel(const PyrArgs a) {
     const float* par = s_par[cur];
     float na = 1.f, nb = 0.f;
     if (a.nin.stats) { const float2 mr = s_mr[sample]; na = par[5 * D + 1] * mr.y; nb = fmaf(-mr.x, na, par[5 * D + 2]); }
+    if constexpr (PC) { if (act) { slope = par[5 * D + 3]; sle1 = slope <= 1.f; } }      // this row's (channel's) own slope
     pyr_mbar_wait(&s_bar[cur], (it >> 1) & 1);
 
     // y[g0-2 .. g0+17] from the row buffer (index 4 + position), then u = PReLU(GLN(y)), 0 outside the row
@@ -672,12 +676,19 @@ int launch_pyramid(const float* y, const NormIn& nin, const float* const* w5, co
         return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
     };
     int rc;
-    if (threads <= 256)      // rows up to 7-8 windows (L <= 3712 / 3328): compiled for several resident CTAs per SM
-        rc = D == 4 ? launch(dw_pyramid_kernel<4, 256, SDR_PYR_MINB>)
-                    : (D == 5 ? launch(dw_pyramid_kernel<5, 256, SDR_PYR_MINB>) : launch(dw_pyramid_kernel<6, 256, SDR_PYR_MINB>));
+    if (nin.prelu && nin.prelu_pc) {
+        if (threads <= 256)
+            rc = D == 4 ? launch(dw_pyramid_kernel<4, 256, SDR_PYR_MINB, true>)
+                        : (D == 5 ? launch(dw_pyramid_kernel<5, 256, SDR_PYR_MINB, true>) : launch(dw_pyramid_kernel<6, 256, SDR_PYR_MINB, true>));
+        else
+            rc = D == 4 ? launch(dw_pyramid_kernel<4, 1024, 1, true>)
+                        : (D == 5 ? launch(dw_pyramid_kernel<5, 1024, 1, true>) : launch(dw_pyramid_kernel<6, 1024, 1, true>));
+    } else if (threads <= 256)      // rows up to 7-8 windows (L <= 3712 / 3328): compiled for several resident CTAs per SM
+        rc = D == 4 ? launch(dw_pyramid_kernel<4, 256, SDR_PYR_MINB, false>)
+                    : (D == 5 ? launch(dw_pyramid_kernel<5, 256, SDR_PYR_MINB, false>) : launch(dw_pyramid_kernel<6, 256, SDR_PYR_MINB, false>));
     else
-        rc = D == 4 ? launch(dw_pyramid_kernel<4, 1024, 1>)
-                    : (D == 5 ? launch(dw_pyramid_kernel<5, 1024, 1>) : launch(dw_pyramid_kernel<6, 1024, 1>));
+        rc = D == 4 ? launch(dw_pyramid_kernel<4, 1024, 1, false>)
+                    : (D == 5 ? launch(dw_pyramid_kernel<5, 1024, 1, false>) : launch(dw_pyramid_kernel<6, 1024, 1, false>));
     if (rc != SDR_OK) return rc;
     pyramid_solve_kernel<<<(unsigned)samples, kSolveThreads, 0, st>>>(s);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;

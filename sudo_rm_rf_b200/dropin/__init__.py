@@ -22,6 +22,7 @@ REDIRECTS = {
     "sudo_rm_rf.dnn.models.improved_sudormrf": "sudo_rm_rf/dnn/models/improved_sudormrf.py",
     "sudo_rm_rf.dnn.models.groupcomm_sudormrf_v2": "sudo_rm_rf/dnn/models/groupcomm_sudormrf_v2.py",
     "sudo_rm_rf.dnn.models.causal_improved_sudormrf_v3": "sudo_rm_rf/dnn/models/causal_improved_sudormrf_v3.py",
+    "sudo_rm_rf.dnn.models.sudormrf": "sudo_rm_rf/dnn/models/sudormrf.py",
     "sudo_rm_rf.dnn.experiments.utils.mixture_consistency":
         "sudo_rm_rf/dnn/experiments/utils/mixture_consistency.py",
 }

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_native.EXPORTED_SYMBOLS)
-    assert lib.sdr_abi_version() == 1
+    assert lib.sdr_abi_version() == _native.ABI_VERSION == 2
     assert lib.sdr_error_string(0) == b"ok"
     assert b"unknown" not in lib.sdr_error_string(-5)
 
@@ -43,9 +43,14 @@ def test_header_symbols_are_exported():
                     enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
     ("causal", dict(in_audio_channels=2, out_channels=16, in_channels=32, num_blocks=3, upsampling_depth=5,
                     enc_kernel_size=11, enc_num_basis=24, num_sources=3)),
+    ("original", dict(out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+                      enc_kernel_size=21, enc_num_basis=512, num_sources=2)),
+    ("original", dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=5,
+                      enc_kernel_size=11, enc_num_basis=32, num_sources=3)),      # out_channels == enc_num_basis: no reshape layer
 ])
 def test_layout_matches_state_dict(variant, kw):
-    cls = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}[variant]
+    cls = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF,
+           "original": P.OriginalSuDORMRF}[variant]
     m = cls(**kw)
     cfg_o = O.Config(variant=variant, **kw)
     sd = m.state_dict()
@@ -54,6 +59,9 @@ def test_layout_matches_state_dict(variant, kw):
     for k, v in sd.items():
         assert tuple(v.shape) == tuple(shapes[k]), k
     cfg = _engine.make_config(m)
+    if variant == "original":          # ln_mask_in is registered last and never read by forward (sudormrf.py:253): not packed
+        assert list(sd.keys())[-2:] == ["ln_mask_in.weight", "ln_mask_in.bias"]
+        sd = {k: v for k, v in list(sd.items())[:-2]}
     assert _engine.state_dict_names(cfg) == list(sd.keys())
     lib = _native.lib()
     assert lib.sdr_num_params(C.byref(cfg)) == len(sd)
@@ -62,7 +70,7 @@ def test_layout_matches_state_dict(variant, kw):
         assert lib.sdr_param_numel(C.byref(cfg), i) == v.numel()
         total += v.numel()
     assert lib.sdr_packed_weight_bytes(C.byref(cfg)) >= 4 * total
-    for T in (1, 100, 320, 321, 32000, 32079):
+    for T in (1, 100, 160, 320, 321, 32000, 32079):
         assert lib.sdr_padded_length(C.byref(cfg), T) == O.padded_length(cfg_o, T)
     assert lib.sdr_workspace_bytes(C.byref(cfg), 2, 32000) > 0
 
@@ -80,6 +88,10 @@ def test_bad_configs_rejected():
     assert lib.sdr_num_params(C.byref(bad)) == -1
     assert lib.sdr_workspace_bytes(C.byref(bad), 1, 100) == 0
     bad = _native.SdrConfig(1, 1, 30, 64, 1, 3, 21, 16, 2, 4)      # Co % G != 0
+    assert lib.sdr_num_params(C.byref(bad)) == -1
+    bad = _native.SdrConfig(3, 1, 16, 32, 1, 3, 21, 25, 2, 1)      # original model, odd basis count: its mask Conv2d returns N + 1 rows
+    assert lib.sdr_num_params(C.byref(bad)) == -1
+    bad = _native.SdrConfig(4, 1, 16, 32, 1, 3, 21, 24, 2, 1)      # no such variant
     assert lib.sdr_num_params(C.byref(bad)) == -1
     with pytest.raises(AssertionError):
         P.GroupCommSudoRmRf(enc_kernel_size=20)

@@ -54,8 +54,9 @@ assert improved_sudormrf.SuDORMRF is P.SuDORMRF, improved_sudormrf.__file__
 assert sudormrf_gc_v2.GroupCommSudoRmRf is P.GroupCommSudoRmRf
 assert mixture_consistency.apply is P.mixture_consistency.apply
 assert causal.CausalSuDORMRF is P.CausalSuDORMRF
+assert initial_sudormrf.SuDORMRF is P.OriginalSuDORMRF and initial_sudormrf.SuDORMRF is not P.SuDORMRF
 # everything else -> the reference's own files
-for mod in (parser, sisdr_lib, initial_sudormrf, snr_lib):
+for mod in (parser, sisdr_lib, snr_lib):
     assert mod.__file__.startswith(ref), mod.__file__
 # the objects the runner builds from them (run_improved_sudormrf.py:66-70,82-85,88-96)
 loss = sisdr_lib.PermInvariantSISDR(batch_size=2, n_sources=2, zero_mean=True, backward_loss=False,

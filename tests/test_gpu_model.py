@@ -15,7 +15,8 @@ DEV = "cuda"
 TOL = 1e-3
 
 
-CLASSES = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}
+CLASSES = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF,
+           "original": P.OriginalSuDORMRF}
 
 
 def build(variant, kw, sd):
@@ -91,8 +92,18 @@ FULL = [
     ("causal_stereo_u4_512_T44099", "causal",
      dict(in_audio_channels=2, out_channels=256, in_channels=512, num_blocks=4, upsampling_depth=5,
           enc_kernel_size=21, enc_num_basis=512, num_sources=2), 1, 44099),
+    # SURVEY 8f.3 sibling variant: the ORIGINAL SuDoRM-RF with its constructor defaults (sudormrf.py:186-193; tensor-core
+    # GEMMs with per-channel PReLU on the operand loads, reshape_before_masks, Toeplitz mask GEMM M = 1024 / K = 512) ...
+    ("original_default_u16_512", "original",
+     dict(out_channels=128, in_channels=512, num_blocks=16, upsampling_depth=4,
+          enc_kernel_size=21, enc_num_basis=512, num_sources=2), 2, 32000),
+    # ... and a three-source model without the reshape layer (out_channels == enc_num_basis), depth 5, odd length
+    ("original_u4_256_3src_T32079", "original",
+     dict(out_channels=256, in_channels=512, num_blocks=4, upsampling_depth=5,
+          enc_kernel_size=21, enc_num_basis=256, num_sources=3), 1, 32079),
 ]
-DEFAULT_TOO = ("cfg2_improved_u16_512", "cfg3_improved_u36_2048", "cfg5_improved_u36_4096_16k")
+DEFAULT_TOO = ("cfg2_improved_u16_512", "cfg3_improved_u36_2048", "cfg5_improved_u36_4096_16k",
+               "original_default_u16_512")
 
 
 @pytest.mark.parametrize("name,variant,kw,B,T", FULL, ids=[f[0] for f in FULL])
@@ -432,3 +443,36 @@ def test_data_parallel_two_devices_sees_new_weights():
             base.load_state_dict(sd)
             y = m(x.cuda(0))
             assert max(O.parity_errors(y, O.forward(cfg, sd, x))) < 1e-4
+
+
+def test_original_model_api():
+    """The original SuDoRM-RF (sudormrf.py) behind its own import path: README-style call, mixture consistency,
+    separate(normalize=True), forward_host with a CUDA graph, lengths that need padding and lengths that do not."""
+    kw = dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+              enc_kernel_size=21, enc_num_basis=48, num_sources=2)
+    cfg = O.Config(variant="original", **kw)
+    sd = O.make_state_dict(cfg, seed=3)
+    m = build("original", kw, sd)
+    assert m.lcm == 80
+    for T in (4001, 4000, 77):                 # 4000 is a multiple of lcm(10, 16) = 80: the reference does not pad it
+        x = torch.randn(3, 1, T, generator=torch.Generator().manual_seed(T))
+        ref = O.forward(cfg, sd, x)
+        with torch.no_grad():
+            y = m(x.to(DEV))
+            ymc = m.separate(x.to(DEV), mixture_consistency=True)
+        assert y.shape == (3, 2, T)
+        assert max(O.parity_errors(y, ref)) < 1e-4
+        assert max(O.parity_errors(ymc, O.mixture_consistency(ref, x))) < 1e-4
+    x = torch.randn(3, 1, 4001, generator=torch.Generator().manual_seed(5)) * 3 + 0.5
+    with torch.no_grad():
+        got = m.separate(x.to(DEV), normalize=True)
+    assert max(O.parity_errors(got, O.separate(cfg, sd, x.squeeze(1)))) < 1e-4
+    hx = x.pin_memory()
+    hy = m.forward_host(hx)
+    for _ in range(2):                         # eager, capture, replay
+        m.forward_host(hx, hy)
+    torch.cuda.synchronize()
+    assert max(O.parity_errors(hy, O.forward(cfg, sd, x))) < 1e-4
+    m.train()
+    with pytest.raises(RuntimeError, match="inference"):
+        m(x.to(DEV))

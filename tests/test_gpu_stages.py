@@ -23,10 +23,20 @@ def stream():
 
 
 def norm_in(stats=None, gamma=None, beta=None, prelu=None, count=1.0):
+    """prelu: 1 element = nn.PReLU(); more = one slope per channel (nn.PReLU(C) of the original model)."""
     return N.SdrNormIn(stats.data_ptr() if stats is not None else 0,
                        gamma.data_ptr() if gamma is not None else 0,
                        beta.data_ptr() if beta is not None else 0,
-                       prelu.data_ptr() if prelu is not None else 0, float(count))
+                       prelu.data_ptr() if prelu is not None else 0, float(count),
+                       1 if prelu is not None and prelu.numel() > 1 else 0)
+
+
+def channel_slopes(C_, g):
+    """Per-channel PReLU slopes on both sides of 1 and of 0."""
+    s = 0.1 + 0.5 * torch.rand(C_, generator=g)
+    r = torch.rand(C_, generator=g)
+    s = torch.where(r < 0.15, torch.full_like(s, -0.2), torch.where(r > 0.8, torch.full_like(s, 1.3), s))
+    return s.to(DEV)
 
 
 def raw_stats(x):
@@ -50,7 +60,9 @@ def close(a, b, tol=2e-5):
 
 def ref_norm(x, gamma, beta, prelu=None):
     y = O.glob_ln(x, gamma, beta)
-    return O.prelu1(y, prelu) if prelu is not None else y
+    if prelu is None:
+        return y
+    return O.prelu_c(y, prelu) if prelu.numel() > 1 else O.prelu1(y, prelu)
 
 
 @pytest.mark.parametrize("samples,C_,L,stride,prelu", [
@@ -59,13 +71,14 @@ def ref_norm(x, gamma, beta, prelu=None):
     (2, 512, 800, 2, False), (4, 5, 4, 1, True),
     (2, 9, 16, 1, False), (2, 9, 16, 2, True), (3, 6, 8, 1, True), (2, 512, 3200, 1, True),
     (2, 33, 6400, 2, False), (1, 4, 40, 1, False),
+    (2, 64, 3200, 1, "pc"), (3, 24, 104, 1, "pc"), (2, 7, 26, 1, "pc"), (2, 9, 16, 2, "pc"),   # nn.PReLU(C) (sudormrf.py:33)
 ])
 def test_depthwise(samples, C_, L, stride, prelu):
     g = torch.Generator().manual_seed(0)
     x = (torch.randn(samples, C_, L, generator=g) * 2 + 0.7).to(DEV)
     gamma = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
     beta = (0.2 * torch.randn(C_, generator=g)).to(DEV)
-    slope = torch.tensor([0.3], device=DEV) if prelu else None
+    slope = channel_slopes(C_, g) if prelu == "pc" else (torch.tensor([0.3], device=DEV) if prelu else None)
     w = torch.randn(C_, 1, 5, generator=g).to(DEV)
     b = torch.randn(C_, generator=g).to(DEV)
     stats_in = raw_stats(x).to(DEV)
@@ -87,6 +100,8 @@ def test_depthwise(samples, C_, L, stride, prelu):
     (5, 32, 3200, 5, True),      # GroupComm rows
     (3, 7, 48, 4, True),         # shortest eligible rows: L >> (D-1) == 6, every run of the merge is an edge run
     (2, 5, 96, 5, False), (2, 3, 192, 6, True), (4, 9, 112, 4, True), (2, 6, 1024, 6, True), (300, 4, 448, 4, True),
+    # one PReLU slope per channel (the original model's UBlock, sudormrf.py:33,171)
+    (2, 512, 3200, 4, "pc"), (3, 64, 3200, 5, "pc"), (1, 32, 6400, 6, "pc"), (3, 7, 48, 4, "pc"), (2, 9, 80, 4, "pc"),
 ])
 def test_depthwise_pyramid(samples, C_, L, D, prelu):
     """sdr_depthwise_pyramid + sdr_merge_pyramid == the level-by-level chain in torch (improved_sudormrf.py:205-216)."""
@@ -95,7 +110,7 @@ def test_depthwise_pyramid(samples, C_, L, D, prelu):
     y = (torch.randn(samples, C_, L, generator=g) * 1.3 + 0.3).to(DEV)
     gy = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
     by = (0.2 * torch.randn(C_, generator=g)).to(DEV)
-    slope = torch.tensor([0.3], device=DEV) if prelu else None
+    slope = channel_slopes(C_, g) if prelu == "pc" else (torch.tensor([0.3], device=DEV) if prelu else None)
     ws = [torch.randn(C_, 1, 5, generator=g).to(DEV) * 0.6 for _ in range(D)]
     bs = [torch.randn(C_, generator=g).to(DEV) * 0.5 for _ in range(D)]
     gs = [(1 + 0.3 * torch.randn(C_, generator=g)).to(DEV) for _ in range(D)]
@@ -215,6 +230,7 @@ def test_merge(samples, C_, L, depth):
     (3, 24, 8, 132, "norm"),              # ... M not a multiple of 16, ragged last quad chunk
     (2, 64, 64, 64, "mask"),              # ... largest shape it takes
     (2, 8, 4, 4, "plain_stats"),
+    (2, 32, 16, 517, "pc"), (2, 24, 32, 52, "pc"), (2, 128, 96, 130, "pc"), (2, 16, 64, 3200, "pc"),   # per-channel PReLU slopes
 ])
 def test_pointwise(samples, M, K, L, mode):
     g = torch.Generator().manual_seed(2)
@@ -233,6 +249,10 @@ def test_pointwise(samples, M, K, L, mode):
     if mode == "norm":
         nin = norm_in(stats_in, gamma, beta, None, K * L)
         fx = ref_norm(x, gamma, beta)
+    elif mode == "pc":
+        slopes = channel_slopes(K, g)
+        nin = norm_in(stats_in, gamma, beta, slopes, K * L)
+        fx = ref_norm(x, gamma, beta, slopes)
     elif mode == "res":
         nin = norm_in(stats_in, gamma, beta, slope, K * L)
         fx = ref_norm(x, gamma, beta, slope)
@@ -256,7 +276,7 @@ def test_pointwise(samples, M, K, L, mode):
     if mode == "mask":
         idx = torch.arange(M, device=DEV) % gate_ch
         want = torch.relu(want) * gate.double()[:, idx, :]
-    want_stats = mode in ("plain_stats",)
+    want_stats = mode in ("plain_stats", "pc")
     N.check(N.lib().sdr_pointwise(p(x), C.byref(nin), p(W), p(bias), res_ptr, p(gate), gate_ch,
                                   p(y), p(st) if want_stats else p(None),
                                   samples, M, K, L, epi, stream()))
@@ -394,6 +414,12 @@ def test_mixture_consistency(kind):
     (3, 256, 256, 36, "res"),             # L < 128 and not a multiple of 32: clipped bulk rows
     (3, 512, 128, 200, "mask"),           # ragged last position tile: zero-filled gate boxes
     (20, 512, 64, 1280, "mask"),          # many tiles per CTA: the gate ring wraps across tile boundaries
+    # per-channel PReLU slopes in the operand transform (the original model, sudormrf.py:33,71)
+    (2, 512, 128, 3200, "pc_stats"),      # its proj_1x1 (Co = 128 -> Ci = 512)
+    (2, 128, 512, 3200, "pc_stats"),      # its conv_1x1_exp
+    (3, 512, 128, 200, "pc"),             # reshape_before_masks, ragged last position tile
+    (40, 1024, 512, 384, "pc"),           # the Toeplitz mask GEMM read through module_act; CTAs loop over many tiles
+    (1, 256, 64, 100, "pc_stats"),        # a single k-block
 ])
 def test_pointwise_tensor_core(samples, M, K, L, mode):
     """tcgen05 path (bf16x3 split, fp32 accumulate) against an fp64 reference."""
@@ -429,6 +455,10 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
         gate_ch = M // 2
         gate = torch.randn(samples, gate_ch, L, generator=g).to(DEV)
         epi = 1
+    elif mode in ("pc", "pc_stats"):
+        slopes = channel_slopes(K, g)
+        nin = norm_in(stats_in, gamma, beta, slopes, K * L)
+        fx = ref_norm(x.double(), gamma.double(), beta.double(), slopes.double())
     else:
         nin = norm_in()
         fx = x.double()
@@ -438,7 +468,7 @@ def test_pointwise_tensor_core(samples, M, K, L, mode):
     if mode == "mask":
         idx = torch.arange(M, device=DEV) % gate_ch
         want = torch.relu(want) * gate.double()[:, idx, :]
-    want_stats = mode == "plain_stats"
+    want_stats = mode in ("plain_stats", "pc_stats")
     N.check(lib.sdr_pointwise_mma(p(x), C.byref(nin), p(wpk), p(bias), p(y) if mode == "res" else (p(residual) if mode == "res_out" else p(None)),
                                   p(gate), gate_ch, p(y), p(st) if want_stats else p(None),
                                   samples, M, K, L, epi, stream()))
@@ -471,3 +501,59 @@ def test_pointwise_tensor_core_eligibility():
     assert lib.sdr_pointwise_mma_packed_bytes(32, 16) == 0         # group-communication blocks
     assert lib.sdr_pointwise_mma_packed_bytes(256, 100) == 0
     assert lib.sdr_pointwise_mma_packed_bytes(512, 256) == 512 * 256 * 4
+
+
+@pytest.mark.parametrize("samples,C_,L,first", [
+    (2, 128, 3200, False), (3, 16, 52, False), (2, 24, 517, True), (1, 7, 3, False), (2, 128, 3200, True),
+])
+def test_residual_norm(samples, C_, L, first):
+    """Tail of the original UBlock (sudormrf.py:184-186): x <- GN(e) + f(x) in place, statistics of the new x;
+    f = identity for the first block, else the previous block's module_act (GroupNorm + per-channel PReLU)."""
+    g = torch.Generator().manual_seed(21)
+    e = (torch.randn(samples, C_, L, generator=g) * 1.7 - 0.4).to(DEV)
+    x = (torch.randn(samples, C_, L, generator=g) * 0.8 + 0.2).to(DEV)
+    ge = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
+    be = (0.2 * torch.randn(C_, generator=g)).to(DEV)
+    gx = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
+    bx = (0.2 * torch.randn(C_, generator=g)).to(DEV)
+    slopes = channel_slopes(C_, g)
+    fe = norm_in(raw_stats(e).to(DEV), ge, be, None, C_ * L)
+    fx = norm_in() if first else norm_in(raw_stats(x).to(DEV), gx, bx, slopes, C_ * L)
+    want = ref_norm(e, ge, be) + (x if first else ref_norm(x, gx, bx, slopes))
+    st = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
+    N.check(N.lib().sdr_residual_norm(p(e), C.byref(fe), p(x), C.byref(fx), p(st), samples, C_, L, stream()))
+    close(x, want)
+    check_stats(st, want)
+
+
+@pytest.mark.parametrize("B,S,N_,L,inplace", [
+    (2, 2, 512, 3200, True), (3, 3, 24, 52, False), (2, 1, 16, 80, True), (1, 4, 7, 3, False), (2, 16, 8, 10, True),
+])
+def test_softmax_gate(B, S, N_, L, inplace):
+    """Masks of the original model (sudormrf.py:285-289): softmax over the sources (sigmoid for one) x encoder output."""
+    g = torch.Generator().manual_seed(22)
+    logits = (torch.randn(B, S, N_, L, generator=g) * 3).to(DEV)
+    enc = torch.relu(torch.randn(B, N_, L, generator=g)).to(DEV)
+    want = (torch.sigmoid(logits) if S == 1 else torch.softmax(logits, dim=1)) * enc.unsqueeze(1)
+    out = logits.clone() if inplace else torch.full_like(logits, float("nan"))
+    N.check(N.lib().sdr_softmax_gate(p(out if inplace else logits), p(enc), p(out), B, S, N_, L, stream()))
+    close(out, want, tol=1e-5)
+
+
+@pytest.mark.parametrize("B,T,N_,K,D", [(2, 32000, 512, 21, 4), (3, 517, 24, 21, 3), (1, 333, 16, 11, 4)])
+def test_original_front_and_back_ends(B, T, N_, K, D):
+    """Biased encoder + ReLU and the biased grouped decoder of the original model (sudormrf.py:212-218,245-252,291)
+    through the whole-model entry: a model with zero blocks is exactly encoder -> ln -> l1 -> Toeplitz mask GEMM ->
+    softmax gate -> decoder GEMM -> overlap-add (tensor-core GEMMs at N = 512, FFMA ones at the small sizes)."""
+    import sudo_rm_rf_b200 as P
+    kw = dict(out_channels=N_, in_channels=2 * N_, num_blocks=0, upsampling_depth=D, enc_kernel_size=K,
+              enc_num_basis=N_, num_sources=2)
+    cfg = O.Config(variant="original", **kw)
+    sd = O.make_state_dict(cfg, seed=13)
+    m = P.OriginalSuDORMRF(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    x = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    close(y, O.forward(cfg, sd, x), tol=1e-4)
