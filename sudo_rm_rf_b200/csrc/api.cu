@@ -56,7 +56,7 @@ int launch_pointwise_mma(const float*, const NormIn&, const void*, const float*,
 
 size_t encoder_mma_packed_bytes(int N, int A, int Kk);
 int pack_encoder_mma(const float* W, int N, int A, int Kk, void* packed, cudaStream_t);
-int launch_encoder_mma(const float*, const void*, float*, double*, int, int, long long, int, int, int, int, cudaStream_t);
+int launch_encoder_mma(const float*, const void*, const float*, int, float*, double*, int, int, long long, int, int, int, int, cudaStream_t);
 
 // One 1x1 convolution: tensor cores when the channel counts fill a tcgen05 tile, FFMA otherwise.
 static int pointwise(const float* x, const NormIn& nin, const float* W, const float* wpk, const float* bias,
@@ -183,7 +183,11 @@ static Layout make_layout(const sdr_config* c) {
         l.rs_pk = l.rs_w ? add_pk(l.N, l.Co) : 0;
         l.mask_pk = add_pk(l.S * l.N, l.N);
         l.dec_pk = add_pk(l.S * l.K, l.S * l.N);
-        l.enc_pk = 0;                                   // biased encoder + ReLU: the FFMA encoder kernel
+        {                                               // biased encoder + ReLU: the window kernel with bias / ReLU on the way out
+            const size_t b = encoder_mma_packed_bytes(l.N, 1, l.K);
+            l.enc_pk = b ? cur : 0;
+            cur += b / sizeof(float);
+        }
         l.mask_a = l.mask_w = l.mask_b = 0;
         l.total = cur;
         l.ok = true;
@@ -365,7 +369,7 @@ static int forward_causal(const Layout& l, const float* pk, const float* mixture
     const NormIn none{nullptr, nullptr, nullptr, nullptr, 1.0};
     // encoder (:194): 2k-1 taps of which the causal mask keeps the first k, i.e. the improved model's encoder reading
     // one hop further into the past (left padding 2 * hop)
-    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
+    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, nullptr, 0, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
     else SDR_TRY(launch_encoder(mixture, pk + l.enc_wc, nullptr, 0, e, nullptr, B, l.A, T, l.N, l.K, L, 2 * l.hop, st));
     SDR_TRY(pointwise(e, none, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
                       x, nullptr, B, l.Co, l.N, L, 0, st));                                      // :199
@@ -413,7 +417,8 @@ static int forward_original(const Layout& l, const float* pk, const float* mixtu
     if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
 
     // front end (:268-276): biased encoder + ReLU (+stats), ln folded into l1's operand load
-    SDR_TRY(launch_encoder(mixture, pk + l.enc_w, pk + l.enc_b, 1, e, slot(0), B, 1, T, N, l.K, L, l.hop, st));
+    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, pk + l.enc_b, 1, e, slot(0), B, 1, T, N, l.K, L, l.hop, st));
+    else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, pk + l.enc_b, 1, e, slot(0), B, 1, T, N, l.K, L, l.hop, st));
     {
         NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)N * L, 0};
         SDR_TRY(pointwise(e, ln, pk + l.bn_w, l.bn_pk ? pk + l.bn_pk : nullptr, pk + l.bn_b, nullptr, nullptr, 0,
@@ -515,7 +520,7 @@ static int forward_impl(const Layout& l, const float* pk, const float* mixture, 
     if (cudaMemsetAsync(stats, 0, p.stats_doubles * sizeof(double), st) != cudaSuccess) return SDR_ERR_CUDA;
 
     // front end: encoder (+stats), ln folded into the bottleneck's operand load
-    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
+    if (l.enc_pk) SDR_TRY(launch_encoder_mma(mixture, pk + l.enc_pk, nullptr, 0, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
     else SDR_TRY(launch_encoder(mixture, pk + l.enc_w, nullptr, 0, e, slot(0), B, l.A, T, l.N, l.K, L, l.hop, st));
     {
         NormIn ln{slot(0), pk + l.ln_g, pk + l.ln_be, nullptr, (double)l.N * L};
@@ -688,6 +693,7 @@ int sdr_pack_weights(const sdr_config* cfg, const float* const* params, int n_pa
         if (l.rs_pk) SDR_TRY(pack_pointwise_mma(pk + l.rs_w, l.N, l.Co, pk + l.rs_pk, st));
         if (l.mask_pk) SDR_TRY(pack_pointwise_mma(pk + l.toep_w, l.S * l.N, l.N, pk + l.mask_pk, st));
         if (l.dec_pk) SDR_TRY(pack_pointwise_mma(pk + l.dec_wt, l.S * l.K, l.S * l.N, pk + l.dec_pk, st));
+        if (l.enc_pk) SDR_TRY(pack_encoder_mma(pk + l.enc_w, l.N, 1, l.K, pk + l.enc_pk, st));
         return SDR_OK;
     }
     const int C = l.S * l.A * l.N, SAK = l.S * l.A * l.K;
@@ -834,7 +840,7 @@ int sdr_encoder_mma_pack(const float* weight, int N, int A, int K, void* packed,
 int sdr_encoder_mma(const float* wav, const void* packed_w, float* enc, double* stats,
                     int B, int A, int64_t T, int N, int K, int L, sdr_stream stream) {
     if (K % 2 == 0) return SDR_ERR_BAD_CONFIG;
-    return launch_encoder_mma(wav, packed_w, enc, stats, B, A, T, N, K, L, K / 2, static_cast<cudaStream_t>(stream));
+    return launch_encoder_mma(wav, packed_w, nullptr, 0, enc, stats, B, A, T, N, K, L, K / 2, static_cast<cudaStream_t>(stream));
 }
 
 int sdr_pointwise(const float* x, const sdr_norm_in* fin, const float* W, const float* bias,

@@ -14,12 +14,17 @@
 // shared memory; each thread produces four consecutive outputs of a level from 4-5 LDS.128 of its input; the
 // merge reads every level once and stores float4.  HBM traffic: y once (+ halo, from L2) and m once,
 // 8 B per (row, position) against the 5 round trips of a level-by-level schedule.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sdr {
 
-constexpr int kCzThreads = 256;
-constexpr int kCzWindow = 2048;      // positions per CTA (upper bound; the host balances the windows of a row)
+constexpr int kCzThreads = 256;      // upper bound; the host picks the block size (a multiple of 32) that leaves the fewest idle lanes
+constexpr int kCzWindow = 4096;      // positions per CTA (upper bound; the host balances the windows of a row).  ncu of the
+                                     // 2 x 1600-position windows of a 3200-position row with 256 threads (profiles/r02b_causal.md):
+                                     // 421 / 209 / 103 / 50 quads per level against 256 lanes = 66 % of the issued lanes useful,
+                                     // barrier the second stall reason; a whole row per CTA with 160 threads: 800 / 400 / 200 / 100
+                                     // quads = 5 / 2.5 / 1.25 / 0.6 passes (90 %), no halo, 6 CTAs per SM
 constexpr int kCzTaps = 11;          // taps that survive the causal mask of a 21-tap filter
 constexpr int kCzFilter = 21;
 constexpr int kCzSlack = 8;          // floats of slack after every level buffer (the last, ragged quad of a level)
@@ -41,7 +46,7 @@ __device__ __forceinline__ float prelu(float v, float s) { return v >= 0.f ? v :
 __global__ void __launch_bounds__(kCzThreads)
 causal_pyramid_kernel(const CausalPyrArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const long long row = blockIdx.x / a.tiles;
     const int tile = (int)(blockIdx.x - row * a.tiles);
     const int c = (int)(row % a.C);
@@ -56,7 +61,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
         const int nq = (Wt + hy) >> 2;
         const float* src = a.y + row * a.L;
         const int g0 = t0 - hy;                         // multiple of 4
-        for (int q = tid; q < nq; q += kCzThreads) {
+        for (int q = tid; q < nq; q += nthr) {
             const int g = g0 + 4 * q;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (g >= 0) {
@@ -85,7 +90,11 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
         const int org = (t0 >> d) - a.h[d];             // global index of out[0]
         const int nq = (n + 3) >> 2;
         if (d == 0) {
-            for (int q = tid; q < nq; q += kCzThreads) {
+            for (int q = tid; q < nq; q += nthr) {
+                if (org + 4 * q + 3 < 0) {                   // left of the row (first window's halo): the padding zeros
+                    *reinterpret_cast<float4*>(out + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    continue;
+                }
                 float x[16];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -103,7 +112,11 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
                 *reinterpret_cast<float4*>(out + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
             }
         } else {
-            for (int q = tid; q < nq; q += kCzThreads) {
+            for (int q = tid; q < nq; q += nthr) {
+                if (org + 4 * q + 3 < 0) {
+                    *reinterpret_cast<float4*>(out + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    continue;
+                }
                 float x[20];
 #pragma unroll
                 for (int v = 0; v < 5; ++v) {
@@ -127,7 +140,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
     // ---- merge: m[t] = sum_d o_d[t >> d], four positions per thread
     {
         float* dst = a.m + row * a.L + t0;
-        for (int q = tid; q < (Wt >> 2); q += kCzThreads) {
+        for (int q = tid; q < (Wt >> 2); q += nthr) {
             const int t = 4 * q;                         // relative to t0 (t0 is a multiple of 4 << (D-1))
             float4 v = *reinterpret_cast<const float4*>(smem + a.off[0] + a.h[0] + t);
             if (D > 1) {
@@ -179,7 +192,22 @@ int launch_causal_pyramid(const float* y, const float* slope_in, const float* co
     }
     const long long grid = (long long)samples * C * a.tiles;
     if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
-    causal_pyramid_kernel<<<(unsigned)grid, kCzThreads, smem, st>>>(a);
+    // block size: the multiple of 32 in [128, 256] with the fewest idle lane-passes over the window's phases
+    int threads = kCzThreads;
+    {
+        long long best = -1;
+        for (int t = kCzThreads; t >= 128; t -= 32) {
+            auto slots = [&](int quads) { return (long long)ceil_div(quads, t) * t; };
+            long long c = slots((a.W + a.h[0] + 12) >> 2) / 3 + slots(a.W >> 2) / 2;       // load and merge passes are short
+            for (int d = 0; d < D; ++d) c += slots(((a.W >> d) + a.h[d] + 3) >> 2);
+            if (best < 0 || c < best) { best = c; threads = t; }
+        }
+    }
+    if (const char* e = getenv("SDR_CZ_THREADS")) {       // measurement override (tools/): 128..256, a multiple of 32
+        const int t = atoi(e);
+        if (t >= 128 && t <= kCzThreads && t % 32 == 0) threads = t;
+    }
+    causal_pyramid_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

@@ -98,11 +98,16 @@ __device__ __forceinline__ void sg_store(float* p, const float (&v)[4]) {
     else *p = v[0];
 }
 
-// one thread: all S sources of 4 (VEC) or 1 positions; reads complete before the first write, so out may alias logits
-template <bool VEC>
+// one thread: all S sources of 4 (VEC) or 1 positions; reads complete before the first write, so out may alias logits.
+// SS: compile-time source count (2, 3, 4: the loops unroll to exactly S loads / exps / stores, ~40 registers); 0 = any S
+// up to kSgMaxSrc (the first version, every S through 16 predicated copies: 92 registers, 557 instructions per warp,
+// 433 us for the 1.05 GB of the default model's masks, profiles/r02b_original.md).
+template <bool VEC, int SS>
 __global__ void __launch_bounds__(256)
-softmax_gate_kernel(const float* logits, const float* __restrict__ enc, float* out, int S, long long NL) {
+softmax_gate_kernel(const float* logits, const float* __restrict__ enc, float* out, int S_rt, long long NL) {
     constexpr int W = VEC ? 4 : 1;
+    constexpr int SMAX = SS ? SS : kSgMaxSrc;
+    const int S = SS ? SS : S_rt;
     const int b = blockIdx.y;
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * W;
     if (i >= NL) return;
@@ -118,12 +123,12 @@ softmax_gate_kernel(const float* logits, const float* __restrict__ enc, float* o
         sg_store<VEC>(op, v);
         return;
     }
-    float v[kSgMaxSrc][4];
+    float v[SMAX][4];
     float mx[4], sum[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) { mx[u] = -INFINITY; sum[u] = 0.f; }
 #pragma unroll
-    for (int s = 0; s < kSgMaxSrc; ++s) {
+    for (int s = 0; s < SMAX; ++s) {
         if (s < S) {
             sg_load<VEC>(lp + (size_t)s * NL, v[s]);
 #pragma unroll
@@ -131,7 +136,7 @@ softmax_gate_kernel(const float* logits, const float* __restrict__ enc, float* o
         }
     }
 #pragma unroll
-    for (int s = 0; s < kSgMaxSrc; ++s) {
+    for (int s = 0; s < SMAX; ++s) {
         if (s < S) {
 #pragma unroll
             for (int u = 0; u < W; ++u) { v[s][u] = expf(v[s][u] - mx[u]); sum[u] += v[s][u]; }
@@ -140,12 +145,22 @@ softmax_gate_kernel(const float* logits, const float* __restrict__ enc, float* o
 #pragma unroll
     for (int u = 0; u < W; ++u) g[u] = g[u] / sum[u];
 #pragma unroll
-    for (int s = 0; s < kSgMaxSrc; ++s) {
+    for (int s = 0; s < SMAX; ++s) {
         if (s < S) {
 #pragma unroll
             for (int u = 0; u < W; ++u) v[s][u] *= g[u];
             sg_store<VEC>(op + (size_t)s * NL, v[s]);
         }
+    }
+}
+
+template <bool VEC>
+static void launch_sg(dim3 grid, const float* logits, const float* enc, float* out, int S, long long NL, cudaStream_t st) {
+    switch (S) {
+        case 2: softmax_gate_kernel<VEC, 2><<<grid, 256, 0, st>>>(logits, enc, out, S, NL); break;
+        case 3: softmax_gate_kernel<VEC, 3><<<grid, 256, 0, st>>>(logits, enc, out, S, NL); break;
+        case 4: softmax_gate_kernel<VEC, 4><<<grid, 256, 0, st>>>(logits, enc, out, S, NL); break;
+        default: softmax_gate_kernel<VEC, 0><<<grid, 256, 0, st>>>(logits, enc, out, S, NL); break;
     }
 }
 
@@ -159,8 +174,8 @@ int launch_softmax_gate(const float* logits, const float* enc, float* out, int B
     const long long gx = (threads + 255) / 256;
     if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)gx, (unsigned)B);
-    if (vec) softmax_gate_kernel<true><<<grid, 256, 0, st>>>(logits, enc, out, S, NL);
-    else     softmax_gate_kernel<false><<<grid, 256, 0, st>>>(logits, enc, out, S, NL);
+    if (vec) launch_sg<true>(grid, logits, enc, out, S, NL, st);
+    else     launch_sg<false>(grid, logits, enc, out, S, NL, st);
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 

@@ -207,6 +207,9 @@ pw_gemm_kernel(const PwArgs a) {
 // warp), 64 FMAs against 16 weights broadcast from shared memory, float4 stores.
 // Requires K <= 64, L % 4 == 0.
 // ---------------------------------------------------------------------------
+#ifndef SDR_PW_TILE
+#define SDR_PW_TILE 1                  // 1: shapes the tile-staged kernel takes (M <= 32, K <= 32) run on it; 0: pw_small_kernel (A/B builds)
+#endif
 constexpr int kSmMaxThreads = 256;
 constexpr int kSmMT = 16;          // output channels per thread (8 per thread, 5 CTAs per SM, measured slower: res_conv shape 72 -> 88 us)
 constexpr int kSmKT = 8;           // input rows whose loads are issued together (8 x 16 B in flight per thread)
@@ -333,6 +336,170 @@ pw_small_kernel(const PwArgs a, int chunks_per_sample) {
     if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
 }
 
+// ---------------------------------------------------------------------------
+// Tile-staged variant of the small-channel kernel (the GroupComm production geometry: 16 -> 32 and 32 -> 16 channels).
+// ncu of pw_small_kernel at cfg 4 (profiles/r02b_groupcomm.md): 124-126 registers -> 15 warps per SM, issue-active
+// 36-46 %, long-scoreboard the top stall, and the two blockIdx.y halves of the 32-output conv re-read their inputs
+// from DRAM (209 MB read for 105 MB of operands): load and FFMA phases of a thread run back to back and there are too
+// few warps to overlap them.  Here the loads leave the registers: a CTA owns P positions of one sample, thread 0 issues
+// ONE bulk TMA copy per input row ([K (+K) rows][P] fp32, up to 40 KB in flight per CTA) while the other threads stage
+// the weights; every thread then owns 2 positions x ALL output channels (inputs by LDS.64, weights by broadcast LDS.128,
+// 2*MT accumulators), so nothing is read twice and 4 CTAs per SM overlap each other's copy, FFMA and store phases.
+// ---------------------------------------------------------------------------
+constexpr int kStMaxRows = 64;         // input rows staged per CTA (K, or 2K with the pre-add operand)
+constexpr int kStMaxK = 32;
+
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+template <bool PRE, int MT>
+__global__ void __launch_bounds__(256)
+pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
+    extern __shared__ __align__(16) float st_buf[];        // [rows][P]
+    __shared__ __align__(16) float sW[kStMaxK][MT];        // [k][m]
+    __shared__ float2 sAB[kStMaxK];                         // folded norm of the operand: y = x*a + b
+    __shared__ float2 sPre[kStMaxK];                        // folded norm of the pre-add operand
+    __shared__ float sBias[MT];
+    __shared__ float s_red[64];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int sample = blockIdx.x / tiles_per_sample;
+    const int p0 = (blockIdx.x - sample * tiles_per_sample) * P;
+    const int np = min(P, a.L - p0);                        // positions of this tile (a multiple of 4)
+    const int rows = PRE ? 2 * a.K : a.K;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&s_bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)np * sizeof(float);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(&s_bar)), "r"(bytes * (uint32_t)rows) : "memory");
+        for (int r = 0; r < rows; ++r) {
+            const float* src = (PRE && r >= a.K) ? a.pre_add + ((size_t)sample * a.K + (r - a.K)) * a.L + p0
+                                                 : a.x + ((size_t)sample * a.K + r) * a.L + p0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st_smem_u32(st_buf + (size_t)r * P)), "l"(src), "r"(bytes), "r"(st_smem_u32(&s_bar)) : "memory");
+        }
+    }
+    for (int i = tid; i < a.K * MT; i += nthr) {
+        const int k = i / MT, m = i - k * MT;
+        sW[k][m] = (m < a.M) ? __ldg(a.W + (size_t)m * a.K + k) : 0.f;
+    }
+    if (tid < MT) sBias[tid] = (a.bias && tid < a.M) ? __ldg(a.bias + tid) : 0.f;
+    if (tid < a.K) {
+        float aa = 1.f, bb = 0.f;
+        if (a.nin.stats) {
+            const SampleNorm sn = sample_norm(a.nin, sample);
+            aa = __ldg(a.nin.gamma + tid) * sn.rstd;
+            bb = fmaf(-sn.mean, aa, __ldg(a.nin.beta + tid));
+        }
+        sAB[tid] = make_float2(aa, bb);
+        float pa = 1.f, pb = 0.f;
+        if (PRE && a.pre_norm.stats) {
+            const SampleNorm sn = sample_norm(a.pre_norm, sample);
+            pa = __ldg(a.pre_norm.gamma + tid) * sn.rstd;
+            pb = fmaf(-sn.mean, pa, __ldg(a.pre_norm.beta + tid));
+        }
+        sPre[tid] = make_float2(pa, pb);
+    }
+    const bool act = a.nin.prelu != nullptr;
+    const float slope = act ? __ldg(a.nin.prelu) : 1.f;
+    __syncthreads();                                        // tables + the initialised barrier are visible
+    {
+        const uint32_t addr = st_smem_u32(&s_bar);
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(addr), "r"(0) : "memory");
+        } while (!done);
+    }
+    const int t2 = 2 * tid;                                 // this thread's 2 positions inside the tile
+    float st_s = 0.f, st_q = 0.f;
+    if (t2 < np) {
+        float acc[MT][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { acc[m][0] = sBias[m]; acc[m][1] = sBias[m]; }
+        const size_t gpos = (size_t)p0 + t2;
+#pragma unroll 2
+        for (int k = 0; k < a.K; ++k) {
+            float2 v = *reinterpret_cast<const float2*>(st_buf + (size_t)k * P + t2);
+            if constexpr (PRE) {                            // operand = x + GlobLN(pre_add); kept for the skip connection
+                const float2 w = *reinterpret_cast<const float2*>(st_buf + (size_t)(a.K + k) * P + t2);
+                const float2 pn = sPre[k];
+                v.x += fmaf(w.x, pn.x, pn.y); v.y += fmaf(w.y, pn.x, pn.y);
+                *reinterpret_cast<float2*>(a.pre_out + ((size_t)sample * a.K + k) * a.L + gpos) = v;
+            }
+            const float2 ab = sAB[k];
+            v.x = fmaf(v.x, ab.x, ab.y); v.y = fmaf(v.y, ab.x, ab.y);
+            if (act) { v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope; }
+#pragma unroll
+            for (int m4 = 0; m4 < MT / 4; ++m4) {
+                const float4 w = *reinterpret_cast<const float4*>(&sW[k][m4 * 4]);
+                acc[m4 * 4 + 0][0] = fmaf(w.x, v.x, acc[m4 * 4 + 0][0]); acc[m4 * 4 + 0][1] = fmaf(w.x, v.y, acc[m4 * 4 + 0][1]);
+                acc[m4 * 4 + 1][0] = fmaf(w.y, v.x, acc[m4 * 4 + 1][0]); acc[m4 * 4 + 1][1] = fmaf(w.y, v.y, acc[m4 * 4 + 1][1]);
+                acc[m4 * 4 + 2][0] = fmaf(w.z, v.x, acc[m4 * 4 + 2][0]); acc[m4 * 4 + 2][1] = fmaf(w.z, v.y, acc[m4 * 4 + 2][1]);
+                acc[m4 * 4 + 3][0] = fmaf(w.w, v.x, acc[m4 * 4 + 3][0]); acc[m4 * 4 + 3][1] = fmaf(w.w, v.y, acc[m4 * 4 + 3][1]);
+            }
+        }
+        const size_t obase = (size_t)sample * a.M * a.L + gpos;
+#pragma unroll
+        for (int m8 = 0; m8 < MT; m8 += 8) {               // 8 output rows at a time: the residual loads of a group in flight together
+            if (a.residual) {                               // may alias y: every element is read by the thread that writes it
+                float2 r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    r[j] = (m8 + j < a.M) ? *reinterpret_cast<const float2*>(a.residual + obase + (size_t)(m8 + j) * a.L)
+                                          : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc[m8 + j][0] += r[j].x; acc[m8 + j][1] += r[j].y; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int m = m8 + j;
+                if (m < a.M) {
+                    *reinterpret_cast<float2*>(a.y + obase + (size_t)m * a.L) = make_float2(acc[m][0], acc[m][1]);
+                    st_s += acc[m][0] + acc[m][1];
+                    st_q = fmaf(acc[m][0], acc[m][0], st_q); st_q = fmaf(acc[m][1], acc[m][1], st_q);
+                }
+            }
+        }
+    }
+    if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
+}
+
+// Tile geometry of pw_tile_kernel: threads = the multiple of 32 in [128, 256] that wastes the fewest threads on rows of
+// L / 2 position pairs; P = 2 * threads positions per CTA.  false: the shape is not taken (the caller uses pw_small_kernel).
+static bool tile_shape(int M, int K, int rows, int L, int epilogue, bool aligned, int* threads_out) {
+    if (!aligned || (L % 4) != 0 || epilogue != 0 || M > 32 || K > kStMaxK || rows > kStMaxRows) return false;
+    int best = 256;
+    long long best_waste = -1;
+    const int pairs = L / 2;
+    for (int t = 256; t >= 128; t -= 32) {
+        const long long waste = (long long)((pairs + t - 1) / t) * t - pairs;
+        if (best_waste < 0 || waste < best_waste) { best = t; best_waste = waste; }
+    }
+    if ((size_t)rows * 2 * best * sizeof(float) > 160 * 1024) return false;
+    *threads_out = best;
+    return true;
+}
+
+template <bool PRE>
+static int launch_tile(const PwArgs& a, int samples, int threads, cudaStream_t st) {
+    const int P = 2 * threads;
+    const int tiles = (a.L + P - 1) / P;
+    const long long gx = (long long)tiles * samples;
+    if (gx > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    const int rows = PRE ? 2 * a.K : a.K;
+    const size_t smem = (size_t)rows * P * sizeof(float);
+    auto go = [&](auto kern) -> int {
+        if (smem > 40 * 1024 &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return SDR_ERR_CUDA;
+        }
+        kern<<<(unsigned)gx, threads, smem, st>>>(a, tiles, P);
+        return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+    };
+    return a.M <= 16 ? go(pw_tile_kernel<PRE, 16>) : go(pw_tile_kernel<PRE, 32>);
+}
+
 // block size for rows of `quads` position quads: the multiple of 32 in [128, 256] that wastes the fewest threads
 static int small_block_threads(int quads) {
     int best = kSmMaxThreads;
@@ -370,7 +537,9 @@ int launch_pointwise_ffma(const float* x, const NormIn& nin, const float* W, con
     if (residual) al |= reinterpret_cast<uintptr_t>(residual);
     if (gate) al |= reinterpret_cast<uintptr_t>(gate);
     const bool vec = (L % 4 == 0) && (al % 16 == 0);
-    if (vec && K <= kSmMaxK && M <= 64 && !nin.prelu_pc) {   // streaming small-channel kernel (one shared PReLU slope)
+    if (vec && K <= kSmMaxK && M <= 64 && !nin.prelu_pc) {   // streaming small-channel kernels (one shared PReLU slope)
+        int tt = 0;
+        if (SDR_PW_TILE && tile_shape(M, K, K, L, epilogue, true, &tt)) return launch_tile<false>(a, samples, tt, st);
         const int threads = small_block_threads(L / 4);
         const int chunks = (L / 4 + threads - 1) / threads;
         const long long gx = (long long)chunks * samples;
@@ -398,6 +567,10 @@ int launch_pointwise_small_preadd(const float* x, const float* pre_add, const No
     a.gate = nullptr; a.gate_channels = 0; a.y = y; a.stats_out = stats_out;
     a.M = M; a.K = K; a.L = L; a.l_tiles = (L + kBN - 1) / kBN; a.epilogue = 0;
     a.pre_add = pre_add; a.pre_norm = pre_norm; a.pre_out = xt_out;
+    {
+        int tt = 0;
+        if (SDR_PW_TILE && tile_shape(M, K, 2 * K, L, 0, true, &tt)) return launch_tile<true>(a, samples, tt, st);
+    }
     const int threads = small_block_threads(L / 4);
     const int chunks = (L / 4 + threads - 1) / threads;
     const long long gx = (long long)chunks * samples;

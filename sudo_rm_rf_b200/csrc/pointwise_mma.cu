@@ -876,6 +876,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
         const int q = warp & 3;             // TMEM lane quarter of this warp
         const int col0 = (warp >> 2) * (a.tile_n / EG);
         const size_t Ls = (size_t)a.L;
+        const bool relu_out = WINDOW && a.epilogue == 2;       // window mode only: ReLU on the way out
         const int nchunks = a.tile_n / kEpiChunk / EG;
         // (the same staged exit for plain stores, mode 0, measured slower than direct stores: proj 104 vs 86 us)
         constexpr bool kBulk = SDR_MMA_BULK && MODE == 3;
@@ -962,6 +963,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                             float o = __uint_as_float(R[j]) + bb[u];
                             if (MODE == 1) o += E[MODE != 0 ? j : 0];
                             if (MODE == 2) o = fmaxf(o, 0.f) * E[MODE != 0 ? j : 0];
+                            if constexpr (WINDOW) { if (relu_out) o = fmaxf(o, 0.f); }   // the original model's encoder (sudormrf.py:212-218)
                             *yp = o;
                             yp += Ls;
                             if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
@@ -978,6 +980,7 @@ pw_mma_kernel(const MmaArgs a, const __grid_constant__ CUtensorMap tmap,      //
                         if (MODE != 0) ev = ep[(size_t)(c * kEpiChunk + j) * Ls];
                         if (MODE == 1) o += ev;
                         if (MODE == 2) o = fmaxf(o, 0.f) * ev;
+                        if constexpr (WINDOW) { if (relu_out) o = fmaxf(o, 0.f); }
                         yp[(size_t)j * Ls] = o;
                         if (STATS) { st_s += o; st_q = fmaf(o, o, st_q); }
                     }
@@ -1288,15 +1291,15 @@ int pack_encoder_mma(const float* W, int N, int A, int Kk, void* packed, cudaStr
     return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
 }
 
-int launch_encoder_mma(const float* wav, const void* wpk, float* enc, double* stats,
+int launch_encoder_mma(const float* wav, const void* wpk, const float* bias, int relu, float* enc, double* stats,
                        int B, int A, long long T, int N, int Kk, int L, int pad, cudaStream_t st) {
     if (!encoder_mma_packed_bytes(N, A, Kk)) return SDR_ERR_UNSUPPORTED;
     if (B <= 0 || T <= 0 || L <= 0 || !wav || !wpk || !enc) return SDR_ERR_BAD_ARGUMENT;
     MmaArgs a;
     a.x = wav; a.nin = NormIn{nullptr, nullptr, nullptr, nullptr, 1.0};
-    a.wpk = static_cast<const uint8_t*>(wpk); a.bias = nullptr; a.residual = nullptr; a.gate = nullptr;
+    a.wpk = static_cast<const uint8_t*>(wpk); a.bias = bias; a.residual = nullptr; a.gate = nullptr;
     a.gate_channels = 0; a.y = enc; a.stats_out = stats;
-    a.M = N; a.K = enc_kpad(A, Kk); a.L = L; a.epilogue = 0;
+    a.M = N; a.K = enc_kpad(A, Kk); a.L = L; a.epilogue = relu ? 2 : 0;      // (window kernels read it as "ReLU on the way out")
 #if SDR_MMA_TRACE
     a.trace = nullptr;
 #endif

@@ -230,6 +230,7 @@ def test_merge(samples, C_, L, depth):
     (3, 24, 8, 132, "norm"),              # ... M not a multiple of 16, ragged last quad chunk
     (2, 64, 64, 64, "mask"),              # ... largest shape it takes
     (2, 8, 4, 4, "plain_stats"),
+    (3, 32, 32, 1604, "norm"), (5, 20, 12, 1604, "res"), (300, 16, 32, 800, "res"),   # tile-staged kernel: ragged last tile, many CTAs
     (2, 32, 16, 517, "pc"), (2, 24, 32, 52, "pc"), (2, 128, 96, 130, "pc"), (2, 16, 64, 3200, "pc"),   # per-channel PReLU slopes
 ])
 def test_pointwise(samples, M, K, L, mode):
@@ -517,8 +518,9 @@ def test_residual_norm(samples, C_, L, first):
     gx = (1 + 0.3 * torch.randn(C_, generator=g)).to(DEV)
     bx = (0.2 * torch.randn(C_, generator=g)).to(DEV)
     slopes = channel_slopes(C_, g)
-    fe = norm_in(raw_stats(e).to(DEV), ge, be, None, C_ * L)
-    fx = norm_in() if first else norm_in(raw_stats(x).to(DEV), gx, bx, slopes, C_ * L)
+    st_e, st_x = raw_stats(e).to(DEV), raw_stats(x).to(DEV)          # (kept alive: the structs hold raw pointers)
+    fe = norm_in(st_e, ge, be, None, C_ * L)
+    fx = norm_in() if first else norm_in(st_x, gx, bx, slopes, C_ * L)
     want = ref_norm(e, ge, be) + (x if first else ref_norm(x, gx, bx, slopes))
     st = torch.zeros(samples, 2, dtype=torch.float64, device=DEV)
     N.check(N.lib().sdr_residual_norm(p(e), C.byref(fe), p(x), C.byref(fx), p(st), samples, C_, L, stream()))

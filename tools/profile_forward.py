@@ -15,8 +15,7 @@ ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--iters", type=int, default=2)
 a = ap.parse_args()
 w = bench.WORKLOADS[a.workload]
-cls = P.SuDORMRF if w["variant"] == "improved" else P.GroupCommSudoRmRf
-m = cls(**w["kw"]).cuda().eval()
+m = bench.model_class(w["variant"])(**w["kw"]).cuda().eval()
 x = torch.rand(a.batch or w["B"], 1, w["T"], device="cuda")
 with torch.no_grad():
     for _ in range(a.iters):
