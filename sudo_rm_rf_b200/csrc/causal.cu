@@ -21,7 +21,7 @@ namespace sdr {
 
 constexpr int kCzThreads = 256;      // upper bound; the host picks the block size (a multiple of 32) that leaves the fewest idle lanes
 constexpr int kCzWindow = 4096;      // positions per CTA (upper bound; the host balances the windows of a row).  ncu of the
-                                     // 2 x 1600-position windows of a 3200-position row with 256 threads (profiles/r02b_causal.md):
+                                     // 2 x 1600-position windows of a 3200-position row with 256 threads (profiles/r02b_kernels.md):
                                      // 421 / 209 / 103 / 50 quads per level against 256 lanes = 66 % of the issued lanes useful,
                                      // barrier the second stall reason; a whole row per CTA with 160 threads: 800 / 400 / 200 / 100
                                      // quads = 5 / 2.5 / 1.25 / 0.6 passes (90 %), no halo, 6 CTAs per SM
@@ -42,6 +42,11 @@ struct CausalPyrArgs {
 };
 
 __device__ __forceinline__ float prelu(float v, float s) { return v >= 0.f ? v : v * s; }
+// PReLU in two instructions: max(v, s*v) for s <= 1, min otherwise (the side of 1 is uniform per level)
+__device__ __forceinline__ float prelu2(float v, float s, bool s_le1) {
+    const float t = v * s;
+    return s_le1 ? fmaxf(v, t) : fminf(v, t);
+}
 
 __global__ void __launch_bounds__(kCzThreads)
 causal_pyramid_kernel(const CausalPyrArgs a) {
@@ -57,6 +62,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
     // ---- y window -> shared memory, PReLU of proj_1x1 applied on the way (zero left of the row: the conv's padding)
     {
         const float sp = __ldg(a.slope_in);
+        const bool sp1 = sp <= 1.f;
         const int hy = a.h[0] + 12;
         const int nq = (Wt + hy) >> 2;
         const float* src = a.y + row * a.L;
@@ -66,7 +72,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (g >= 0) {
                 v = ldg4(src + g);
-                v.x = prelu(v.x, sp); v.y = prelu(v.y, sp); v.z = prelu(v.z, sp); v.w = prelu(v.w, sp);
+                v.x = prelu2(v.x, sp, sp1); v.y = prelu2(v.y, sp, sp1); v.z = prelu2(v.z, sp, sp1); v.w = prelu2(v.w, sp, sp1);
             }
             *reinterpret_cast<float4*>(smem + 4 * q) = v;
         }
@@ -84,6 +90,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
         for (int j = 0; j < kCzTaps; ++j) w[j] = __ldg(wp + j);
         const float bias = __ldg(a.b[d] + c);
         const float sl = __ldg(a.slope[d]);
+        const bool sl1 = sl <= 1.f;
         const float* in = d == 0 ? smem : smem + a.off[d - 1];
         float* out = smem + a.off[d];
         const int n = (Wt >> d) + a.h[d];               // outputs of this level in the window (halo included)
@@ -107,7 +114,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
                     float acc = bias;
 #pragma unroll
                     for (int j = 0; j < kCzTaps; ++j) acc = fmaf(w[j], x[u + 2 + j], acc);
-                    o[u] = (org + 4 * q + u >= 0) ? prelu(acc, sl) : 0.f;
+                    o[u] = prelu2(acc, sl, sl1);            // (org is a multiple of 4: a quad is entirely left of the row, skipped above, or inside)
                 }
                 *reinterpret_cast<float4*>(out + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -129,7 +136,7 @@ causal_pyramid_kernel(const CausalPyrArgs a) {
                     float acc = bias;
 #pragma unroll
                     for (int j = 0; j < kCzTaps; ++j) acc = fmaf(w[j], x[2 * u + 2 + j], acc);
-                    o[u] = (org + 4 * q + u >= 0) ? prelu(acc, sl) : 0.f;
+                    o[u] = prelu2(acc, sl, sl1);            // (org is a multiple of 4: a quad is entirely left of the row, skipped above, or inside)
                 }
                 *reinterpret_cast<float4*>(out + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -192,17 +199,10 @@ int launch_causal_pyramid(const float* y, const float* slope_in, const float* co
     }
     const long long grid = (long long)samples * C * a.tiles;
     if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
-    // block size: the multiple of 32 in [128, 256] with the fewest idle lane-passes over the window's phases
-    int threads = kCzThreads;
-    {
-        long long best = -1;
-        for (int t = kCzThreads; t >= 128; t -= 32) {
-            auto slots = [&](int quads) { return (long long)ceil_div(quads, t) * t; };
-            long long c = slots((a.W + a.h[0] + 12) >> 2) / 3 + slots(a.W >> 2) / 2;       // load and merge passes are short
-            for (int d = 0; d < D; ++d) c += slots(((a.W >> d) + a.h[d] + 3) >> 2);
-            if (best < 0 || c < best) { best = c; threads = t; }
-        }
-    }
+    // block size: measured at the default model's rows (L = 3200, D = 4, one window per row, 6 CTAs per SM by shared
+    // memory): 128 / 160 / 192 / 224 / 256 threads = 206 / 192 / 187 / 193 / 196 us; short windows take fewer threads
+    int threads = 192;
+    while (threads > 128 && (a.W >> 2) < threads) threads -= 32;
     if (const char* e = getenv("SDR_CZ_THREADS")) {       // measurement override (tools/): 128..256, a multiple of 32
         const int t = atoi(e);
         if (t >= 128 && t <= kCzThreads && t % 32 == 0) threads = t;

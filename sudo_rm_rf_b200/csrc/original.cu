@@ -101,7 +101,7 @@ __device__ __forceinline__ void sg_store(float* p, const float (&v)[4]) {
 // one thread: all S sources of 4 (VEC) or 1 positions; reads complete before the first write, so out may alias logits.
 // SS: compile-time source count (2, 3, 4: the loops unroll to exactly S loads / exps / stores, ~40 registers); 0 = any S
 // up to kSgMaxSrc (the first version, every S through 16 predicated copies: 92 registers, 557 instructions per warp,
-// 433 us for the 1.05 GB of the default model's masks, profiles/r02b_original.md).
+// 433 us for the 1.05 GB of the default model's masks, profiles/r02b_kernels.md).
 template <bool VEC, int SS>
 __global__ void __launch_bounds__(256)
 softmax_gate_kernel(const float* logits, const float* __restrict__ enc, float* out, int S_rt, long long NL) {

@@ -338,7 +338,7 @@ pw_small_kernel(const PwArgs a, int chunks_per_sample) {
 
 // ---------------------------------------------------------------------------
 // Tile-staged variant of the small-channel kernel (the GroupComm production geometry: 16 -> 32 and 32 -> 16 channels).
-// ncu of pw_small_kernel at cfg 4 (profiles/r02b_groupcomm.md): 124-126 registers -> 15 warps per SM, issue-active
+// ncu of pw_small_kernel at cfg 4 (profiles/r02b_kernels.md): 124-126 registers -> 15 warps per SM, issue-active
 // 36-46 %, long-scoreboard the top stall, and the two blockIdx.y halves of the 32-output conv re-read their inputs
 // from DRAM (209 MB read for 105 MB of operands): load and FFMA phases of a thread run back to back and there are too
 // few warps to overlap them.  Here the loads leave the registers: a CTA owns P positions of one sample, thread 0 issues
@@ -351,8 +351,17 @@ constexpr int kStMaxK = 32;
 
 __device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+constexpr int kStThreads = 160;        // block size bound (the launcher picks 128 or 160)
+#ifndef SDR_ST_MINB32
+#define SDR_ST_MINB32 3                // resident CTAs per SM the 32-outputs-per-thread instantiations are compiled for (4: 96 registers
+#endif                                 // with 300 B of spills, 77 us against 69 us at the cfg-4 proj shape)
+#ifndef SDR_ST_MINB16
+#define SDR_ST_MINB16 4                // ... and the 16-outputs-per-thread ones (4 / 5 / 6: 62.8 / 64.8 / 66.4 us at the cfg-4 res_conv shape)
+#endif
+// (A persistent version with a double buffer - the next tile's copy in flight during the FFMA loop, 2 CTAs per SM by
+//  shared memory - measured 92 / 73 us against 69 / 63 us for one tile per CTA: profiles/r02b_kernels.md.)
 template <bool PRE, int MT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kStThreads, MT == 32 ? SDR_ST_MINB32 : SDR_ST_MINB16)
 pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
     extern __shared__ __align__(16) float st_buf[];        // [rows][P]
     __shared__ __align__(16) float sW[kStMaxK][MT];        // [k][m]
@@ -417,6 +426,19 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
 #pragma unroll
         for (int m = 0; m < MT; ++m) { acc[m][0] = sBias[m]; acc[m][1] = sBias[m]; }
         const size_t gpos = (size_t)p0 + t2;
+        const size_t obase = (size_t)sample * a.M * a.L + gpos;
+        // 16 outputs per thread (every res_conv of a GroupComm block): the skip-connection rows are fetched BEFORE the
+        // FFMA loop and consumed after it (ncu: the epilogue's adds sat on the long scoreboard of these loads).
+        // They may alias y: every element is read by the thread that writes it.
+        float2 rpre[MT == 16 ? 16 : 1];
+        if constexpr (MT == 16) {
+            if (a.residual) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    rpre[m] = (m < a.M) ? *reinterpret_cast<const float2*>(a.residual + obase + (size_t)m * a.L)
+                                        : make_float2(0.f, 0.f);
+            }
+        }
 #pragma unroll 2
         for (int k = 0; k < a.K; ++k) {
             float2 v = *reinterpret_cast<const float2*>(st_buf + (size_t)k * P + t2);
@@ -438,10 +460,15 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
                 acc[m4 * 4 + 3][0] = fmaf(w.w, v.x, acc[m4 * 4 + 3][0]); acc[m4 * 4 + 3][1] = fmaf(w.w, v.y, acc[m4 * 4 + 3][1]);
             }
         }
-        const size_t obase = (size_t)sample * a.M * a.L + gpos;
+        if constexpr (MT == 16) {
+            if (a.residual) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) { acc[m][0] += rpre[m].x; acc[m][1] += rpre[m].y; }
+            }
+        }
 #pragma unroll
         for (int m8 = 0; m8 < MT; m8 += 8) {               // 8 output rows at a time: the residual loads of a group in flight together
-            if (a.residual) {                               // may alias y: every element is read by the thread that writes it
+            if (MT != 16 && a.residual) {                   // may alias y: every element is read by the thread that writes it
                 float2 r[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -468,10 +495,10 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
 // L / 2 position pairs; P = 2 * threads positions per CTA.  false: the shape is not taken (the caller uses pw_small_kernel).
 static bool tile_shape(int M, int K, int rows, int L, int epilogue, bool aligned, int* threads_out) {
     if (!aligned || (L % 4) != 0 || epilogue != 0 || M > 32 || K > kStMaxK || rows > kStMaxRows) return false;
-    int best = 256;
+    int best = kStThreads;
     long long best_waste = -1;
     const int pairs = L / 2;
-    for (int t = 256; t >= 128; t -= 32) {
+    for (int t = kStThreads; t >= 128; t -= 32) {
         const long long waste = (long long)((pairs + t - 1) / t) * t - pairs;
         if (best_waste < 0 || waste < best_waste) { best = t; best_waste = waste; }
     }

@@ -17,7 +17,7 @@ for spec in "$@"; do
   name=${spec%%=*}; flags=${spec#*=}
   bdir=$(mktemp -d)
   echo "== $name: $flags"
-  for f in api pointwise pointwise_mma levels pyramid causal frontback tac prepost; do
+  for f in api pointwise pointwise_mma levels pyramid causal original frontback tac prepost; do
     nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
          --expt-relaxed-constexpr -Xptxas -v $flags -c "$CSRC/$f.cu" -o "$bdir/$f.o" 2> "$bdir/$f.log" &
   done
