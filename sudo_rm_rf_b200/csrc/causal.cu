@@ -51,6 +51,8 @@ __device__ __forceinline__ float prelu2(float v, float s, bool s_le1) {
 __global__ void __launch_bounds__(kCzThreads)
 causal_pyramid_kernel(const CausalPyrArgs a) {
     extern __shared__ __align__(16) float smem[];
+    // (Staging the 13 parameters of every level in 512 B of static shared memory instead of 13 __ldg per level and thread
+    //  measured 222 us against 199 us: the extra bytes cost the sixth resident CTA, profiles/r02b_kernels.md.)
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long row = blockIdx.x / a.tiles;
     const int tile = (int)(blockIdx.x - row * a.tiles);
