@@ -543,8 +543,14 @@ struct MergePyrArgs {
     const float* table;
     int D, C, L;
 };
-constexpr int kMpThreads = 128;
-constexpr int kMpItems = 2;
+#ifndef SDR_MP_THREADS
+#define SDR_MP_THREADS 128
+#endif
+#ifndef SDR_MP_ITEMS
+#define SDR_MP_ITEMS 4                 // runs of 16 outputs per thread (1 / 2 / 4 on one box: 116.2 / 108.7 / 104.7 us at cfg 2; 256 threads x 1: 130.9)
+#endif
+constexpr int kMpThreads = SDR_MP_THREADS;
+constexpr int kMpItems = SDR_MP_ITEMS;
 
 __global__ void __launch_bounds__(kMpThreads)
 merge_pyramid_kernel(const MergePyrArgs a, float* __restrict__ m, double* __restrict__ stats_out, int chunks_per_sample) {
