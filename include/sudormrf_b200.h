@@ -293,6 +293,19 @@ int sdr_pit_sisdr(const float* est, const float* target, const float* mixture_or
                   int zero_mean, int improvement, double eps,
                   void* scratch, sdr_stream stream);
 
+/* StabilizedPermInvSISDRMetric.forward (dnn/losses/sisdr.py:460-591; backward_loss=False,
+ * return_individual_results=True), the validation metric of run_fuss_separation.py:111-131: n_est estimated sources
+ * scored against n_act <= n_est actual ones with the stabilised SI-SNR
+ *     rho^2 = <e,t>^2 / (<e,e><t,t> + eps),  10 log10((rho^2 + eps) / (1 - rho^2 + eps)),
+ * best[b] = max over itertools.permutations(range(n_est), r=n_act) of the source mean (minus, for improvement != 0,
+ * the batch mean of the same figure for the mixture = sum of the targets), perm_index[b] = index of that assignment.
+ * est [B, est_rows, T], target [B, n_act, T]; est_rows == n_est, or est_rows > n_est == 1: single_source mode, the
+ * rows are summed first (:576-577).  1 <= n_act <= n_est <= 4.  eps as in the reference's forward (1e-9).            */
+size_t sdr_stabilized_sisdr_scratch_bytes(int B, int n_est, int n_act);
+int sdr_stabilized_sisdr(const float* est, const float* target, float* best, int32_t* perm_index,
+                         int B, int est_rows, int n_est, int n_act, int64_t T,
+                         int zero_mean, int improvement, double eps, void* scratch, sdr_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

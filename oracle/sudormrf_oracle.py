@@ -15,7 +15,7 @@ reference tree (``/root/reference``):
   sudormrf.py            = sudo_rm_rf/dnn/models/sudormrf.py (the original SuDoRM-RF, variant "original")
   mixture_consistency.py = sudo_rm_rf/dnn/experiments/utils/mixture_consistency.py
   README.md              = the reference's README (inference recipe, lines 100-114)
-  sisdr.py               = sudo_rm_rf/dnn/losses/sisdr.py (validation metric)
+  sisdr.py               = sudo_rm_rf/dnn/losses/sisdr.py (validation metrics)
 
 Parity pinning: the reference ships NO golden vectors for this path,
 so the oracle is pinned against outputs of the reference itself, generated in
@@ -656,6 +656,41 @@ def pit_sisdr(pr: Tensor, tgt: Tensor, mix: Optional[Tensor] = None, zero_mean: 
     if improvement:                                                       # sisdr.py:145-150
         base = permuted(mix.repeat(1, S, 1), tgt, tt)
         best = best - base.mean()
+    return best, idx
+
+
+def stabilized_pit_sisdr(pr: Tensor, tgt: Tensor, zero_mean: bool = False, single_source: bool = False,
+                         improvement: bool = False, eps: float = 1e-9):
+    """StabilizedPermInvSISDRMetric.forward with backward_loss=False, return_individual_results=True
+    (sisdr.py:460-591): n_estimated = pr.shape[1] >= n_actual = tgt.shape[1]; the metric of every validation set of
+    run_fuss_separation.py:111-131.  Returns (best [B], index of the best assignment [B]) with the assignments in
+    itertools.permutations(range(n_estimated), r=n_actual) order (sisdr.py:490-492)."""
+    import itertools
+    if single_source:                                                     # sisdr.py:576-577
+        pr = torch.sum(pr, -2, keepdim=True)
+    if zero_mean:                                                         # sisdr.py:498-502, 579-580
+        pr = pr - pr.mean(-1, keepdim=True)
+        tgt = tgt - tgt.mean(-1, keepdim=True)
+
+    def dot(a, b):                                                        # sisdr.py:504-506
+        return torch.sum(a * b, dim=-1, keepdim=True)
+
+    def stabilized(p, t, tt):                                             # sisdr.py:508-515
+        pp = dot(p, p)
+        rho_sq = dot(p, t) ** 2 / (pp * tt + eps)
+        return 10 * torch.log10((rho_sq + eps) / (1. - rho_sq + eps))
+
+    n_est, n_act = pr.shape[1], tgt.shape[1]
+    assert n_est >= n_act
+    tt = dot(tgt, tgt)                                                    # sisdr.py:524
+    cols = [stabilized(pr[:, list(perm), :], tgt, tt)                     # sisdr.py:526-532
+            for perm in itertools.permutations(range(n_est), r=n_act)]
+    best, idx = torch.max(torch.cat(cols, -1).mean(-2), -1)               # sisdr.py:533
+    if improvement:                                                       # sisdr.py:535-541: the mixture is the sum of the targets
+        mix = torch.sum(tgt, -2, keepdim=True)
+        if zero_mean:
+            mix = mix - mix.mean(-1, keepdim=True)
+        best = best - stabilized(mix.repeat(1, n_act, 1), tgt, tt).mean()
     return best, idx
 
 

@@ -106,6 +106,9 @@ _SIGNATURES = {
     "sdr_pit_sisdr_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "sdr_pit_sisdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "sdr_stabilized_sisdr_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "sdr_stabilized_sisdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

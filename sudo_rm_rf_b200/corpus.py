@@ -29,23 +29,40 @@ def padded_length(T: int, quantum: int) -> int:
     return quantum if T < quantum else -(-T // quantum) * quantum
 
 
-def plan_buckets(lengths: Sequence[int], quantum: int, max_batch: int) -> List[Tuple[int, List[int]]]:
+def plan_buckets(lengths: Sequence[int], quantum, max_batch: int) -> List[Tuple[int, List[int]]]:
     """Groups utterance indices into batches that share a padded length.
 
+    ``quantum``: ``hop * 2**upsampling_depth`` (the improved / GroupComm / causal rule above), or a callable
+    ``T -> padded length`` (the model's own rule, e.g. the original model's lcm padding, sudormrf.py:283-293).
     Returns ``[(padded_length, [indices...]), ...]``: buckets in increasing padded length, inside a
     bucket the corpus order is kept and batches hold at most ``max_batch`` utterances.  Pure host
     logic (deterministic, no torch)."""
     if max_batch < 1:
         raise ValueError("max_batch must be >= 1")
+    pad = quantum if callable(quantum) else (lambda T: padded_length(T, quantum))
     buckets = {}
     for i, T in enumerate(lengths):
-        buckets.setdefault(padded_length(int(T), quantum), []).append(i)
+        if int(T) <= 0:
+            raise ValueError("empty utterance")
+        buckets.setdefault(int(pad(int(T))), []).append(i)
     plan = []
     for Tp in sorted(buckets):
         idx = buckets[Tp]
         for k in range(0, len(idx), max_batch):
             plan.append((Tp, idx[k:k + max_batch]))
     return plan
+
+
+def model_padding_rule(cfg):
+    """``T -> padded length`` of the model behind ``cfg`` (the library's ``sdr_padded_length``: one rule for all variants)."""
+    lib = N.lib()
+
+    def pad(T: int) -> int:
+        Tp = lib.sdr_padded_length(C.byref(cfg), int(T))
+        if Tp <= 0:
+            raise N.NativeError("sdr_padded_length failed (bad model configuration or empty utterance)")
+        return int(Tp)
+    return pad
 
 
 def separate_corpus(model, wavs: Iterable[torch.Tensor], max_batch: int = 32,
@@ -67,13 +84,12 @@ def separate_corpus(model, wavs: Iterable[torch.Tensor], max_batch: int = 32,
     cfg = _engine.make_config(model)
     if cfg.in_audio_channels != 1:
         raise RuntimeError("separate_corpus follows the README recipe, which is written for mono mixtures")
-    device = _engine._fetch(model, "encoder.weight").device
+    device = _engine._fetch(model, _engine._probe_names(model)[0]).device
     if device.type != "cuda":
         raise RuntimeError("sudo_rm_rf_b200 runs on CUDA (sm_100a) only: move the model to a B200")
     if torch.is_grad_enabled() and model.training:
         raise RuntimeError("sudo_rm_rf_b200 implements the inference forward only: call model.eval()")
-    quantum = (cfg.enc_kernel_size // 2) * (2 ** cfg.upsampling_depth)
-    plan = plan_buckets([int(w.shape[0]) for w in wavs], quantum, max_batch)
+    plan = plan_buckets([int(w.shape[0]) for w in wavs], model_padding_rule(cfg), max_batch)
     results: List[torch.Tensor] = [None] * len(wavs)
     S = cfg.num_sources
     with torch.cuda.device(device), torch.no_grad():
@@ -158,10 +174,10 @@ class CorpusSeparator:
         self.cfg = _engine.make_config(model)
         if self.cfg.in_audio_channels != 1:
             raise RuntimeError("CorpusSeparator follows the README recipe, which is written for mono mixtures")
-        self.device = _engine._fetch(model, "encoder.weight").device
+        self.device = _engine._fetch(model, _engine._probe_names(model)[0]).device
         if self.device.type != "cuda":
             raise RuntimeError("sudo_rm_rf_b200 runs on CUDA (sm_100a) only: move the model to a B200")
-        self.quantum = (self.cfg.enc_kernel_size // 2) * (2 ** self.cfg.upsampling_depth)
+        self.quantum = model_padding_rule(self.cfg)      # T -> padded length (the model's own rule)
         self.graphs = {}           # (B, Tp, slot) -> "warm" | CUDAGraph
         self.launches = {"eager": 0, "captured": 0, "replayed": 0}
 

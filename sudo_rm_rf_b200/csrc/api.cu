@@ -44,6 +44,9 @@ int launch_grouped_decoder(const float*, float*, int, int, int, cudaStream_t);
 int launch_utterance_stats(const float*, double*, float2*, int, long long, const long long*, cudaStream_t);
 int launch_normalize_rows(const float*, const float2*, float*, int, long long, const long long*, cudaStream_t);
 size_t pit_sisdr_scratch_bytes(int B, int S);
+size_t stabilized_sisdr_scratch_bytes(int B, int n_est, int n_act);
+int launch_stabilized_sisdr(const float*, const float*, float*, int*, int, int, int, int, long long, int, int, double, void*,
+                            cudaStream_t);
 int launch_pairwise_neg_sdr(const float*, const float*, float*, int, int, long long, int, int, int, void*, cudaStream_t);
 int launch_pit_sisdr(const float*, const float*, const float*, float*, int*, int, int, long long, int, int, double,
                      void*, cudaStream_t);
@@ -1018,6 +1021,16 @@ int sdr_pit_sisdr(const float* est, const float* target, const float* mixture_or
     if (scratch && reinterpret_cast<uintptr_t>(scratch) % 8) return SDR_ERR_BAD_ARGUMENT;
     return launch_pit_sisdr(est, target, mixture_or_null, best, perm_index, B, S, T, zero_mean, improvement, eps,
                             scratch, static_cast<cudaStream_t>(stream));
+}
+
+size_t sdr_stabilized_sisdr_scratch_bytes(int B, int n_est, int n_act) { return stabilized_sisdr_scratch_bytes(B, n_est, n_act); }
+
+int sdr_stabilized_sisdr(const float* est, const float* target, float* best, int32_t* perm_index, int B, int est_rows,
+                         int n_est, int n_act, int64_t T, int zero_mean, int improvement, double eps,
+                         void* scratch, sdr_stream stream) {
+    if (scratch && reinterpret_cast<uintptr_t>(scratch) % 8) return SDR_ERR_BAD_ARGUMENT;
+    return launch_stabilized_sisdr(est, target, best, perm_index, B, est_rows, n_est, n_act, T, zero_mean, improvement, eps,
+                                   scratch, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

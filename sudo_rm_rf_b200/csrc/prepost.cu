@@ -335,6 +335,204 @@ int launch_pairwise_neg_sdr(const float* est, const float* tgt, float* out, int 
     }
 }
 
+// ---------------------------------------------------------------------------
+// StabilizedPermInvSISDRMetric (sisdr.py:460-591), the validation metric of run_fuss_separation.py:111-131:
+// SE estimated sources against SA <= SE actual ones,
+//     rho^2 = <e,t>^2 / (<e,e> <t,t> + eps),  sisnr = 10 log10((rho^2 + eps) / (1 - rho^2 + eps))    (:508-515)
+// best source-mean over the assignments itertools.permutations(range(SE), r=SA) (:490-492,526-533); for the
+// improvement the mixture is the SUM of the (mean-removed) targets (:535-541), so its inner products are sums of the
+// target Gram <t_j, t_k>, which this pass therefore keeps in full.  single_source (:576-577): the `rows` estimate rows
+// of an item are summed on load and scored as one source.
+// Layout of acc[b]: sums e[SE], t[SA]; ET[SE*SA] (i*SA+j); EE[SE]; TT[SA*SA].
+// ---------------------------------------------------------------------------
+template <int SE, int SA> struct StabLayout {
+    static constexpr int V = SE + SA;
+    static constexpr int ET = V, EE = ET + SE * SA, TT = EE + SE, N = TT + SA * SA;
+};
+
+template <int SE, int SA>
+__global__ void __launch_bounds__(256)
+stab_gram_kernel(const float* __restrict__ est, const float* __restrict__ tgt, double* __restrict__ acc,
+                 long long T, int chunks, int rows) {
+    using P = StabLayout<SE, SA>;
+    __shared__ double red[8][P::N];
+    const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
+    const long long per = (T + chunks - 1) / chunks;
+    const long long t0 = (long long)chunk * per;
+    const long long t1 = t0 + per < T ? t0 + per : T;
+    double a[P::N];
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) a[i] = 0.0;
+    const float* eb = est + (size_t)b * rows * T;
+    const float* tb = tgt + (size_t)b * SA * T;
+    for (long long t = t0 + threadIdx.x; t < t1; t += 256) {
+        double e[SE], g[SA];
+        if (SE == 1 && rows > 1) {                         // single_source: the estimates are summed first (fp32, as torch.sum)
+            float sum = 0.f;
+            for (int r = 0; r < rows; ++r) sum += __ldg(eb + (size_t)r * T + t);
+            e[0] = (double)sum;
+        } else {
+#pragma unroll
+            for (int i = 0; i < SE; ++i) e[i] = (double)__ldg(eb + (size_t)i * T + t);
+        }
+#pragma unroll
+        for (int j = 0; j < SA; ++j) g[j] = (double)__ldg(tb + (size_t)j * T + t);
+#pragma unroll
+        for (int i = 0; i < SE; ++i) {
+            a[i] += e[i];
+            a[P::EE + i] = fma(e[i], e[i], a[P::EE + i]);
+#pragma unroll
+            for (int j = 0; j < SA; ++j) a[P::ET + i * SA + j] = fma(e[i], g[j], a[P::ET + i * SA + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < SA; ++j) {
+            a[SE + j] += g[j];
+#pragma unroll
+            for (int k = 0; k < SA; ++k) a[P::TT + j * SA + k] = fma(g[j], g[k], a[P::TT + j * SA + k]);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) {
+        const double v = warp_sum_f64(a[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P::N; i += 256) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][i];
+        atomicAdd(acc + (size_t)b * P::N + i, v);
+    }
+}
+
+__device__ __forceinline__ double stab_sisnr(double et, double ee, double tt, double eps) {
+    const double rho = et * et / (ee * tt + eps);
+    return 10.0 * log10((rho + eps) / (1.0 - rho + eps));
+}
+
+// one block; thread-strided over the batch.  best[b], perm[b] (index in itertools.permutations(range(SE), r=SA) order)
+template <int SE, int SA>
+__global__ void __launch_bounds__(256)
+stab_finalize_kernel(const double* __restrict__ acc, float* __restrict__ best, int* __restrict__ perm,
+                     int B, long long T, int zero_mean, int improvement, double eps) {
+    using P = StabLayout<SE, SA>;
+    __shared__ double red[8];
+    __shared__ double s_base;
+    const double n = (double)T;
+    double base_sum = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        const double* a = acc + (size_t)b * P::N;
+        double me[SE], mt[SA];
+#pragma unroll
+        for (int i = 0; i < SE; ++i) me[i] = zero_mean ? a[i] / n : 0.0;
+#pragma unroll
+        for (int j = 0; j < SA; ++j) mt[j] = zero_mean ? a[SE + j] / n : 0.0;
+        double tt[SA][SA], sn[SE][SA];
+#pragma unroll
+        for (int j = 0; j < SA; ++j)
+#pragma unroll
+            for (int k = 0; k < SA; ++k) tt[j][k] = a[P::TT + j * SA + k] - n * mt[j] * mt[k];
+#pragma unroll
+        for (int i = 0; i < SE; ++i) {
+            const double ee = a[P::EE + i] - n * me[i] * me[i];
+#pragma unroll
+            for (int j = 0; j < SA; ++j)
+                sn[i][j] = stab_sisnr(a[P::ET + i * SA + j] - n * me[i] * mt[j], ee, tt[j][j], eps);
+        }
+        // assignments p[0..SA) of distinct estimates, lexicographic (= itertools.permutations(range(SE), r=SA))
+        double bestv = -1e300;
+        int besti = 0, idx = 0;
+        int total = 1;
+#pragma unroll
+        for (int j = 0; j < SA; ++j) total *= SE;
+        for (int code = 0; code < total; ++code) {
+            int p[SA], c = code;
+            bool ok = true;
+#pragma unroll
+            for (int j = SA - 1; j >= 0; --j) { p[j] = c % SE; c /= SE; }      // p[0] is the most significant digit
+#pragma unroll
+            for (int j = 0; j < SA; ++j)
+#pragma unroll
+                for (int k = 0; k < SA; ++k) if (k < j && p[k] == p[j]) ok = false;
+            if (!ok) continue;
+            double m = 0.0;
+#pragma unroll
+            for (int j = 0; j < SA; ++j) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < SE; ++i) if (p[j] == i) v = sn[i][j];
+                m += v;
+            }
+            m /= (double)SA;
+            if (m > bestv) { bestv = m; besti = idx; }     // torch.max keeps the first maximum
+            ++idx;
+        }
+        best[b] = (float)bestv;
+        perm[b] = besti;
+        if (improvement) {                                  // mixture = sum of the targets
+            double mm = 0.0;
+#pragma unroll
+            for (int j = 0; j < SA; ++j)
+#pragma unroll
+                for (int k = 0; k < SA; ++k) mm += tt[j][k];
+#pragma unroll
+            for (int j = 0; j < SA; ++j) {
+                double mtj = 0.0;
+#pragma unroll
+                for (int k = 0; k < SA; ++k) mtj += tt[k][j];
+                base_sum += stab_sisnr(mtj, mm, tt[j][j], eps);
+            }
+        }
+    }
+    if (!improvement) return;
+    base_sum = warp_sum_f64(base_sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = base_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_base = t / ((double)B * SA);             // base_sisdr.mean(): over the whole batch (sisdr.py:541)
+    }
+    __syncthreads();
+    const double base = s_base;
+    for (int b = threadIdx.x; b < B; b += 256) best[b] = (float)((double)best[b] - base);
+}
+
+template <int SE, int SA>
+static int launch_stab(const float* est, const float* tgt, float* best, int* perm, int B, int rows, long long T,
+                       int zero_mean, int improvement, double eps, double* acc, cudaStream_t st) {
+    using P = StabLayout<SE, SA>;
+    if (cudaMemsetAsync(acc, 0, sizeof(double) * P::N * B, st) != cudaSuccess) return SDR_ERR_CUDA;
+    int chunks = (int)((T + 4095) / 4096);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    const long long grid = (long long)B * chunks;
+    if (grid > 0x7fffffffLL) return SDR_ERR_UNSUPPORTED;
+    stab_gram_kernel<SE, SA><<<(unsigned)grid, 256, 0, st>>>(est, tgt, acc, T, chunks, rows);
+    stab_finalize_kernel<SE, SA><<<1, 256, 0, st>>>(acc, best, perm, B, T, zero_mean, improvement, eps);
+    return cudaGetLastError() == cudaSuccess ? SDR_OK : SDR_ERR_CUDA;
+}
+
+size_t stabilized_sisdr_scratch_bytes(int B, int n_est, int n_act) {
+    if (B <= 0 || n_est < 1 || n_est > 4 || n_act < 1 || n_act > n_est) return 0;
+    return sizeof(double) * (size_t)B * (n_est + n_act + n_est * n_act + n_est + n_act * n_act);
+}
+
+int launch_stabilized_sisdr(const float* est, const float* tgt, float* best, int* perm, int B, int rows, int n_est,
+                            int n_act, long long T, int zero_mean, int improvement, double eps, void* scratch,
+                            cudaStream_t st) {
+    if (!est || !tgt || !best || !perm || !scratch || B <= 0 || T <= 0 || rows < 1) return SDR_ERR_BAD_ARGUMENT;
+    if (rows != n_est && n_est != 1) return SDR_ERR_BAD_ARGUMENT;          // summing the rows is the single_source mode
+    if (!stabilized_sisdr_scratch_bytes(B, n_est, n_act)) return SDR_ERR_UNSUPPORTED;
+    double* acc = static_cast<double*>(scratch);
+#define SDR_STAB(E, A) if (n_est == E && n_act == A) \
+        return launch_stab<E, A>(est, tgt, best, perm, B, rows, T, zero_mean, improvement, eps, acc, st);
+    SDR_STAB(1, 1) SDR_STAB(2, 1) SDR_STAB(2, 2) SDR_STAB(3, 1) SDR_STAB(3, 2) SDR_STAB(3, 3)
+    SDR_STAB(4, 1) SDR_STAB(4, 2) SDR_STAB(4, 3) SDR_STAB(4, 4)
+#undef SDR_STAB
+    return SDR_ERR_UNSUPPORTED;
+}
+
 size_t pit_sisdr_scratch_bytes(int B, int S) {
     if (B <= 0 || S < 1 || S > 4) return 0;
     const int V = 2 * S + 1;

@@ -1,4 +1,4 @@
-"""B200-native mirror of the evaluation metric in ``sudo_rm_rf/dnn/losses/sisdr.py``.
+"""B200-native mirror of the evaluation metrics in ``sudo_rm_rf/dnn/losses/sisdr.py``.
 
 ``PermInvariantSISDR`` keeps the reference's constructor arguments, ``forward``
 signature and return conventions (sisdr.py:66-194), but it is the *metric* the
@@ -76,6 +76,74 @@ class PermInvariantSISDR(nn.Module):
                 1 if self.perform_zero_mean else 0, 1 if self.improvement else 0, float(eps),
                 C.c_void_p(scratch.data_ptr()),
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "sdr_pit_sisdr")
+        result = best if self.return_individual_results else best.mean()
+        if self.backward_loss:
+            result = -result
+        if return_best_permutation:
+            return result, self.permutations_tensor.to(dev)[perm.long()]
+        return result
+
+
+class StabilizedPermInvSISDRMetric(nn.Module):
+    """Stabilised permutation-invariant SI-SDR(i) with more estimated than actual sources (sisdr.py:460-591), the
+    validation metric of ``run_fuss_separation.py:111-131``: same constructor, ``forward`` signature and return
+    conventions as the reference class.  Metric only (no autograd); one fp64 Gram pass + an assignment search per item
+    in ``libsudormrf_b200.so`` (``sdr_stabilized_sisdr``).  Up to 4 estimated sources."""
+
+    def __init__(self, zero_mean=False, single_source=False, n_estimated_sources=None, n_actual_sources=None,
+                 backward_loss=True, improvement=False, return_individual_results=False):
+        super().__init__()
+        self.perform_zero_mean = zero_mean
+        self.backward_loss = backward_loss
+        self.improvement = improvement
+        self.n_estimated_sources = n_estimated_sources
+        self.n_actual_sources = n_actual_sources
+        assert self.n_estimated_sources >= self.n_actual_sources, (
+            'Estimates need to be at least: {} but got: {}'.format(
+                self.n_actual_sources, self.n_estimated_sources))
+        self.permutations = list(itertools.permutations(
+            torch.arange(self.n_estimated_sources), r=self.n_actual_sources))
+        self.permutations_tensor = torch.LongTensor(self.permutations)
+        self.return_individual_results = return_individual_results
+        self.single_source = single_source
+        if self.single_source:
+            assert self.n_actual_sources == 1
+
+    def forward(self, pr_batch, t_batch, eps=1e-9, return_best_permutation=False):
+        """pr_batch ``[B, n_estimated (any number when single_source), T]``, t_batch ``[B, n_actual, T]``."""
+        if pr_batch.dim() != 3 or t_batch.dim() != 3 or pr_batch.shape[0] != t_batch.shape[0] \
+                or pr_batch.shape[-1] != t_batch.shape[-1]:
+            raise RuntimeError("expected pr_batch [B, n_estimated, T] and t_batch [B, n_actual, T]")
+        if t_batch.shape[1] != self.n_actual_sources:
+            raise RuntimeError(f"expected {self.n_actual_sources} actual sources, got {t_batch.shape[1]}")   # sisdr.py:521
+        if not self.single_source and pr_batch.shape[1] != self.n_estimated_sources:
+            raise RuntimeError(f"expected {self.n_estimated_sources} estimated sources, got {pr_batch.shape[1]}")
+        if self.single_source and self.n_estimated_sources != 1:
+            raise RuntimeError("single_source sums the estimates into one: construct the metric with "
+                               "n_estimated_sources=1 (the reference's permutation table indexes the summed tensor)")
+        if not (pr_batch.is_cuda and t_batch.is_cuda):
+            raise RuntimeError("sudo_rm_rf_b200.sisdr runs on CUDA tensors only (no CPU path)")
+        if torch.is_grad_enabled() and (pr_batch.requires_grad or t_batch.requires_grad):
+            raise RuntimeError("sudo_rm_rf_b200.sisdr is the evaluation metric only (no autograd): "
+                               "wrap the call in torch.no_grad()")
+        dev = pr_batch.device
+        est = pr_batch.detach().to(torch.float32).contiguous()
+        tgt = t_batch.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, rows, T = est.shape
+        lib = N.lib()
+        nbytes = lib.sdr_stabilized_sisdr_scratch_bytes(B, self.n_estimated_sources, self.n_actual_sources)
+        if nbytes == 0:
+            raise N.NativeError("sdr_stabilized_sisdr supports 1 <= n_actual <= n_estimated <= 4 sources")
+        with torch.cuda.device(dev):
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            best = torch.empty(B, dtype=torch.float32, device=dev)
+            perm = torch.empty(B, dtype=torch.int32, device=dev)
+            N.check(lib.sdr_stabilized_sisdr(
+                C.c_void_p(est.data_ptr()), C.c_void_p(tgt.data_ptr()), C.c_void_p(best.data_ptr()),
+                C.c_void_p(perm.data_ptr()), B, rows, self.n_estimated_sources, self.n_actual_sources, T,
+                1 if self.perform_zero_mean else 0, 1 if self.improvement else 0, float(eps),
+                C.c_void_p(scratch.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "sdr_stabilized_sisdr")
         result = best if self.return_individual_results else best.mean()
         if self.backward_loss:
             result = -result

@@ -135,7 +135,48 @@ def make_pairwise():
     print(f"pairwise: {ci} cases -> {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def make_stabilized():
+    """``prepost_stabilized.npz``: ``StabilizedPermInvSISDRMetric`` (dnn/losses/sisdr.py:460-591), the validation
+    metric of run_fuss_separation.py:111-131: more estimated than actual sources, one source, single_source (the
+    estimates are summed first), with / without zero-mean and improvement."""
+    arrays, cases = {}, []
+    g = torch.Generator().manual_seed(777)
+    for ci, (n_est, n_act, B, T, zero_mean, improvement, single) in enumerate([
+            (4, 2, 4, 3000, True, True, False), (4, 3, 3, 2000, True, True, False), (4, 4, 2, 1500, True, True, False),
+            (3, 1, 3, 1234, False, False, False), (2, 2, 3, 800, False, True, False), (1, 1, 2, 600, True, False, False),
+            (3, 1, 2, 900, True, False, True), (4, 1, 2, 500, False, False, False)]):
+        tgt = torch.randn(B, n_act, T, generator=g) * (0.2 + torch.rand(B, n_act, 1, generator=g)) + 0.05
+        est = torch.randn(B, n_est, T, generator=g) * 0.05                       # inactive outputs: low-level noise
+        # single_source sums the estimates first (sisdr.py:576-577), so the constructor is given ONE estimated source
+        # (its permutation table indexes the summed tensor, :490-492,527); the model still returned n_est outputs
+        ctor_est = 1 if single else n_est
+        for b in range(B):
+            slots = torch.randperm(n_est, generator=g)[:n_act]
+            for j in range(n_act):
+                est[b, slots[j]] += 0.8 * tgt[b, j] + torch.randn(T, generator=g) * float(10 ** (-2.0 + 1.5 * b / max(1, B - 1)))
+        fn = ref_sisdr.StabilizedPermInvSISDRMetric(zero_mean=zero_mean, single_source=single, n_estimated_sources=ctor_est,
+                                                    n_actual_sources=n_act, backward_loss=False, improvement=improvement,
+                                                    return_individual_results=True)
+        with torch.no_grad():
+            best, perms = fn(est, tgt, return_best_permutation=True)
+        loss = ref_sisdr.StabilizedPermInvSISDRMetric(zero_mean=zero_mean, single_source=single,
+                                                      n_estimated_sources=ctor_est, n_actual_sources=n_act, backward_loss=True,
+                                                      improvement=improvement, return_individual_results=False)
+        with torch.no_grad():
+            scalar = loss(est, tgt)
+        k = f"c{ci}/"
+        arrays.update({k + "est": est.numpy(), k + "tgt": tgt.numpy(), k + "best": best.numpy(),
+                       k + "perms": perms.numpy(), k + "loss": scalar.reshape(1).numpy()})
+        cases.append(dict(n_est=n_est, n_act=n_act, B=B, T=T, zero_mean=zero_mean, improvement=improvement,
+                          single_source=single))
+        print(f"stabilized/c{ci}: {n_est}->{n_act} best={best.numpy().round(3)} perms={perms.numpy().tolist()}")
+    arrays["meta"] = np.frombuffer(json.dumps(dict(cases=cases, torch=torch.__version__)).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, "prepost_stabilized.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"stabilized -> {os.path.getsize(path)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    make_separate()
-    make_sisdr()
-    make_pairwise()
+    todo = sys.argv[1:] or ["separate", "sisdr", "pairwise", "stabilized"]       # name a subset to leave the other fixtures alone
+    for name in todo:
+        {"separate": make_separate, "sisdr": make_sisdr, "pairwise": make_pairwise, "stabilized": make_stabilized}[name]()

@@ -59,3 +59,14 @@ def test_wav_roundtrip(tmp_path):
     wavfile.write(p16, 16000, (x[0].numpy() * 32767).astype(np.int16))
     y, sr = Cp.load_wav(p16)
     assert sr == 16000 and y.shape == (1, 1234) and float((y[0] - x[0]).abs().max()) < 1e-4
+
+
+def test_plan_with_a_model_specific_padding_rule():
+    """The original model pads to multiples of lcm(hop, 2^D) and leaves exact multiples alone (sudormrf.py:283-293)."""
+    cfg = O.Config(variant="original", enc_kernel_size=21, upsampling_depth=4)
+    rule = lambda T: O.padded_length(cfg, T)
+    lengths = [1, 79, 80, 81, 160, 161, 4000, 4001]
+    plan = plan_buckets(lengths, rule, 8)
+    assert [(tp, idx) for tp, idx in plan] == [(80, [0, 1, 2]), (160, [3, 4]), (240, [5]), (4000, [6]), (4080, [7])]
+    with pytest.raises(ValueError):
+        plan_buckets([5, 0], rule, 8)

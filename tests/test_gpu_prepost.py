@@ -20,7 +20,8 @@ TOL = 1e-3
 
 
 def build(variant, kw, sd):
-    cls = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF}[variant]
+    cls = {"improved": P.SuDORMRF, "groupcomm": P.GroupCommSudoRmRf, "causal": P.CausalSuDORMRF,
+           "original": P.OriginalSuDORMRF}[variant]
     m = cls(**kw)
     m.load_state_dict(sd)
     return m.to(DEV).eval()
@@ -127,6 +128,69 @@ def test_pit_sisdr_golden(ci):
     assert abs(float(scalar) - float(t["loss"][0])) < 1e-3
 
 
+def _stabilized_cases():
+    import json
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prepost_stabilized.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return [(c, {n: torch.from_numpy(z[f"c{ci}/" + n]) for n in ("est", "tgt", "best", "perms", "loss")})
+            for ci, c in enumerate(meta["cases"])]
+
+
+@pytest.mark.parametrize("ci", range(8))
+def test_stabilized_sisdr_golden(ci):
+    """sisdr.StabilizedPermInvSISDRMetric (same constructor / forward as dnn/losses/sisdr.py:460-591) against outputs of
+    the reference class: 4 -> 2 / 3 / 4 and 3 / 4 -> 1 sources, single_source, zero-mean and improvement on and off."""
+    c, t = _stabilized_cases()[ci]
+    n_est = 1 if c["single_source"] else c["n_est"]
+    fn = S.StabilizedPermInvSISDRMetric(zero_mean=c["zero_mean"], single_source=c["single_source"],
+                                        n_estimated_sources=n_est, n_actual_sources=c["n_act"], backward_loss=False,
+                                        improvement=c["improvement"], return_individual_results=True)
+    with torch.no_grad():
+        best, perms = fn(t["est"].to(DEV), t["tgt"].to(DEV), return_best_permutation=True)
+    assert best.shape == t["best"].shape and best.is_cuda
+    assert torch.allclose(best.cpu(), t["best"], atol=2e-3, rtol=0), (best.cpu() - t["best"]).abs().max()
+    assert torch.equal(perms.cpu(), t["perms"])
+    loss = S.StabilizedPermInvSISDRMetric(zero_mean=c["zero_mean"], single_source=c["single_source"],
+                                          n_estimated_sources=n_est, n_actual_sources=c["n_act"], backward_loss=True,
+                                          improvement=c["improvement"], return_individual_results=False)
+    with torch.no_grad():
+        scalar = loss(t["est"].to(DEV), t["tgt"].to(DEV))
+    assert abs(float(scalar) - float(t["loss"][0])) < 2e-3
+
+
+def test_stabilized_sisdr_fuss_validation_shape_vs_oracle():
+    """run_fuss_separation.py:111-131,280-310: 4 estimated sources against 1..4 actual ones, 10 s @ 16 kHz, zero-mean,
+    SI-SDRi for more than one actual source; against the CPU oracle, plus argument errors."""
+    g = torch.Generator().manual_seed(5)
+    B, T = 6, 160000
+    for n_act in (1, 2, 3, 4):
+        tgt = torch.randn(B, n_act, T, generator=g) * (0.3 + torch.rand(B, n_act, 1, generator=g))
+        est = 0.03 * torch.randn(B, 4, T, generator=g)
+        for b in range(B):
+            slots = torch.randperm(4, generator=g)[:n_act]
+            for j in range(n_act):
+                est[b, slots[j]] += tgt[b, j] + torch.randn(T, generator=g) * float(10 ** (-1.5 + 0.3 * b))
+        fn = S.StabilizedPermInvSISDRMetric(zero_mean=True, single_source=False, n_estimated_sources=4,
+                                            n_actual_sources=n_act, backward_loss=False, improvement=n_act > 1,
+                                            return_individual_results=True)
+        with torch.no_grad():
+            best, perms = fn(est.to(DEV), tgt.to(DEV), return_best_permutation=True)
+        want, idx = O.stabilized_pit_sisdr(est.double(), tgt.double(), zero_mean=True, improvement=n_act > 1)
+        assert torch.allclose(best.cpu().double(), want, atol=2e-3, rtol=0), (n_act, best.cpu(), want)
+        assert torch.equal(perms.cpu(), fn.permutations_tensor[idx])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fn(est, tgt)
+    with pytest.raises(RuntimeError, match="actual"):
+        fn(est.to(DEV), tgt[:, :2].to(DEV))
+    with pytest.raises(AssertionError):
+        S.StabilizedPermInvSISDRMetric(n_estimated_sources=2, n_actual_sources=3)
+    five = S.StabilizedPermInvSISDRMetric(n_estimated_sources=5, n_actual_sources=2)
+    with torch.no_grad(), pytest.raises(N.NativeError):
+        five(torch.zeros(1, 5, 50, device=DEV), torch.zeros(1, 2, 50, device=DEV))
+
+
 def test_pit_sisdr_full_size_vs_oracle_and_permutation_property():
     """Validation-loop shape (32 x 2 x 4 s): against the CPU oracle, and permuting the estimates'
     source order must permute the reported assignment and leave the score unchanged."""
@@ -171,6 +235,10 @@ CORPUS_MODELS = [
                       enc_kernel_size=21, enc_num_basis=64, num_sources=2)),
     ("groupcomm", dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
                        enc_kernel_size=21, enc_num_basis=48, num_sources=3, group_size=4)),
+    ("causal", dict(in_audio_channels=1, out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,
+                    enc_kernel_size=21, enc_num_basis=48, num_sources=2)),
+    ("original", dict(out_channels=32, in_channels=64, num_blocks=2, upsampling_depth=4,      # buckets by ITS padding rule:
+                      enc_kernel_size=21, enc_num_basis=48, num_sources=2)),                   # multiples of lcm(10, 16) = 80
 ]
 
 
@@ -183,7 +251,7 @@ def test_separate_corpus_equals_one_at_a_time(variant, kw, mc):
     cfg = O.Config(variant=variant, **kw)
     sd = O.make_state_dict(cfg, seed=5, perturbed=True)
     m = build(variant, kw, sd)
-    q = cfg.n_least_samples_req
+    q = O.padded_length(cfg, 1)                # the model's padding quantum (hop * 2^D; lcm(hop, 2^D) for the original model)
     g = torch.Generator().manual_seed(17)
     lengths = [q, q - 1, 1500, 1501, 1502, 37, 2 * q, 2 * q + 1, 5000, 4999, 1499, q + 3, 4990]
     wavs = [torch.randn(T, generator=g) * (0.1 + 3 * torch.rand(1, generator=g)) + 0.1 * torch.randn(1, generator=g)

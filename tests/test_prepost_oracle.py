@@ -108,3 +108,23 @@ def test_pairwise_neg_sdr_matches_reference_golden():
         assert torch.equal(pw, t["pw"]), meta               # same torch op sequence: bit-exact
         loss, _ = O.pit_from_pairwise(pw)
         assert torch.allclose(loss.mean(), t["pit_loss"], rtol=1e-6, atol=1e-6), meta
+
+
+def load_stabilized():
+    z = np.load(os.path.join(GOLDEN_DIR, "prepost_stabilized.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return [(c, {n: torch.from_numpy(z[f"c{ci}/" + n]) for n in ("est", "tgt", "best", "perms", "loss")})
+            for ci, c in enumerate(meta["cases"])]
+
+
+@pytest.mark.parametrize("ci", range(8))
+def test_stabilized_sisdr_matches_reference_golden(ci):
+    """StabilizedPermInvSISDRMetric (sisdr.py:460-591): more estimated than actual sources, single_source, SI-SDRi."""
+    c, t = load_stabilized()[ci]
+    best, idx = O.stabilized_pit_sisdr(t["est"], t["tgt"], zero_mean=c["zero_mean"], single_source=c["single_source"],
+                                       improvement=c["improvement"])
+    assert torch.allclose(best, t["best"], atol=1e-4, rtol=0)
+    n_est = 1 if c["single_source"] else c["n_est"]
+    perms = list(itertools.permutations(range(n_est), r=c["n_act"]))
+    assert [perms[int(i)] for i in idx] == [tuple(int(v) for v in row) for row in t["perms"]]
+    assert torch.allclose(-best.mean(), t["loss"][0], atol=1e-4, rtol=0)
