@@ -448,9 +448,11 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
                 v.x += fmaf(w.x, pn.x, pn.y); v.y += fmaf(w.y, pn.x, pn.y);
                 *reinterpret_cast<float2*>(a.pre_out + ((size_t)sample * a.K + k) * a.L + gpos) = v;
             }
-            const float2 ab = sAB[k];
-            v.x = fmaf(v.x, ab.x, ab.y); v.y = fmaf(v.y, ab.x, ab.y);
-            if (act) { v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope; }
+            if constexpr (!PRE) {                           // (the pre-add operand is never normalised again: launch_pointwise_small_preadd)
+                const float2 ab = sAB[k];
+                v.x = fmaf(v.x, ab.x, ab.y); v.y = fmaf(v.y, ab.x, ab.y);
+                if (act) { v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope; }
+            }
 #pragma unroll
             for (int m4 = 0; m4 < MT / 4; ++m4) {
                 const float4 w = *reinterpret_cast<const float4*>(&sW[k][m4 * 4]);
@@ -466,6 +468,19 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
                 for (int m = 0; m < 16; ++m) { acc[m][0] += rpre[m].x; acc[m][1] += rpre[m].y; }
             }
         }
+        const bool want_stats = a.stats_out != nullptr;
+        if (a.M == MT && (MT == 16 || !a.residual)) {       // every row real, nothing left to add: pointer-bumped stores
+            float* yp = a.y + obase;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                *reinterpret_cast<float2*>(yp) = make_float2(acc[m][0], acc[m][1]);
+                yp += a.L;
+                if (want_stats) {
+                    st_s += acc[m][0] + acc[m][1];
+                    st_q = fmaf(acc[m][0], acc[m][0], st_q); st_q = fmaf(acc[m][1], acc[m][1], st_q);
+                }
+            }
+        } else {
 #pragma unroll
         for (int m8 = 0; m8 < MT; m8 += 8) {               // 8 output rows at a time: the residual loads of a group in flight together
             if (MT != 16 && a.residual) {                   // may alias y: every element is read by the thread that writes it
@@ -486,6 +501,7 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
                     st_q = fmaf(acc[m][0], acc[m][0], st_q); st_q = fmaf(acc[m][1], acc[m][1], st_q);
                 }
             }
+        }
         }
     }
     if (a.stats_out) block_stats_atomic(st_s, st_q, a.stats_out, sample, s_red);
