@@ -439,14 +439,21 @@ pw_tile_kernel(const PwArgs a, int tiles_per_sample, int P) {
                                         : make_float2(0.f, 0.f);
             }
         }
+        // row cursors bumped per input channel (the compiler re-derived the 64-bit global address of every pre_out row)
+        const float* xs = st_buf + t2;
+        const float* os = st_buf + (size_t)a.K * P + t2;
+        float* pre_p = PRE ? a.pre_out + (size_t)sample * a.K * a.L + gpos : nullptr;
 #pragma unroll 2
         for (int k = 0; k < a.K; ++k) {
-            float2 v = *reinterpret_cast<const float2*>(st_buf + (size_t)k * P + t2);
+            float2 v = *reinterpret_cast<const float2*>(xs);
+            xs += P;
             if constexpr (PRE) {                            // operand = x + GlobLN(pre_add); kept for the skip connection
-                const float2 w = *reinterpret_cast<const float2*>(st_buf + (size_t)(a.K + k) * P + t2);
+                const float2 w = *reinterpret_cast<const float2*>(os);
+                os += P;
                 const float2 pn = sPre[k];
                 v.x += fmaf(w.x, pn.x, pn.y); v.y += fmaf(w.y, pn.x, pn.y);
-                *reinterpret_cast<float2*>(a.pre_out + ((size_t)sample * a.K + k) * a.L + gpos) = v;
+                *reinterpret_cast<float2*>(pre_p) = v;
+                pre_p += a.L;
             }
             if constexpr (!PRE) {                           // (the pre-add operand is never normalised again: launch_pointwise_small_preadd)
                 const float2 ab = sAB[k];
