@@ -146,3 +146,60 @@ def test_prepost_entry_points_have_no_cpu_path():
     assert lib.sdr_pit_sisdr_scratch_bytes(4, 2) > 0 and lib.sdr_pit_sisdr_scratch_bytes(4, 5) == 0
     cfg = _native.SdrConfig(0, 1, 16, 32, 1, 2, 21, 16, 2, 1)
     assert lib.sdr_separate_workspace_bytes(C.byref(cfg), 2, 100) > lib.sdr_workspace_bytes(C.byref(cfg), 2, 100)
+
+
+def test_sibling_variants_host_conventions():
+    """The original and the causal model mirrors on the CPU side: constructor defaults and attributes of the reference
+    (sudormrf.py:186-209, causal_improved_sudormrf_v3.py:121-140), state_dict round trip incl. the unused ln_mask_in,
+    whole-module pickle, no CPU path, parameter containers are not callable on their own."""
+    import io
+    m = P.OriginalSuDORMRF()
+    assert (m.out_channels, m.in_channels, m.num_blocks, m.upsampling_depth, m.enc_kernel_size, m.enc_num_basis,
+            m.num_sources) == (128, 512, 16, 4, 21, 512, 2)
+    assert m.lcm == 80 and P.OriginalSuDORMRF(upsampling_depth=5, enc_kernel_size=11).lcm == 160
+    small = dict(out_channels=16, in_channels=32, num_blocks=2, upsampling_depth=3, enc_kernel_size=21,
+                 enc_num_basis=24, num_sources=2)
+    m = P.OriginalSuDORMRF(**small)
+    cfg = O.Config(variant="original", **small)
+    sd = O.make_state_dict(cfg, seed=2)
+    m.load_state_dict(sd)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert hasattr(m, "reshape_before_masks") and not hasattr(P.OriginalSuDORMRF(32, 64, 1, 3, 21, 32, 2), "reshape_before_masks")
+    x = torch.zeros(2, 1, 517)
+    assert m.pad_to_appropriate_length(x).shape[-1] == 520 and m.pad_to_appropriate_length(x[..., :480]) is not None
+    assert m.pad_to_appropriate_length(x[..., :480]).shape[-1] == 480          # a multiple of the lcm is left alone (:284-285)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(x)
+    with pytest.raises(NotImplementedError):
+        m.sm[0](torch.zeros(1, 16, 10))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    assert type(m2) is P.OriginalSuDORMRF and list(m2.state_dict().keys()) == list(sd.keys())
+    c = P.CausalSuDORMRF()
+    assert (c.in_audio_channels, c.out_channels, c.in_channels, c.num_blocks, c.upsampling_depth) == (1, 128, 512, 16, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        c.eval()(torch.zeros(1, 1, 400))
+    # odd basis count: the reference's mask Conv2d then returns N + 1 rows and its forward fails; here the library refuses
+    odd = P.OriginalSuDORMRF(16, 32, 1, 3, 21, 25, 2)
+    assert _native.lib().sdr_num_params(C.byref(_engine.make_config(odd))) == -1
+
+
+def test_stabilized_metric_host_conventions():
+    from sudo_rm_rf_b200 import sisdr
+    fn = sisdr.StabilizedPermInvSISDRMetric(zero_mean=True, n_estimated_sources=4, n_actual_sources=2, backward_loss=False,
+                                            improvement=True, return_individual_results=True)
+    assert len(fn.permutations) == 12 and tuple(int(i) for i in fn.permutations[1]) == (0, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fn(torch.zeros(1, 4, 10), torch.zeros(1, 2, 10))
+    with pytest.raises(RuntimeError, match="actual"):
+        fn(torch.zeros(1, 4, 10), torch.zeros(1, 3, 10))
+    with pytest.raises(AssertionError):
+        sisdr.StabilizedPermInvSISDRMetric(n_estimated_sources=1, n_actual_sources=2)
+    with pytest.raises(AssertionError):
+        sisdr.StabilizedPermInvSISDRMetric(single_source=True, n_estimated_sources=2, n_actual_sources=2)
+    lib = _native.lib()
+    assert lib.sdr_stabilized_sisdr_scratch_bytes(3, 4, 2) == 8 * 3 * (4 + 2 + 8 + 4 + 4)
+    assert lib.sdr_stabilized_sisdr_scratch_bytes(3, 2, 3) == 0 and lib.sdr_stabilized_sisdr_scratch_bytes(3, 5, 2) == 0
