@@ -476,3 +476,18 @@ def test_original_model_api():
     m.train()
     with pytest.raises(RuntimeError, match="inference"):
         m(x.to(DEV))
+
+
+@pytest.mark.parametrize("depth,T", [(1, 1290), (2, 1300), (3, 1324)])
+def test_original_model_shallow_depths_with_unaligned_frame_counts(depth, T):
+    """upsampling_depth 1 / 2 / 3 with lcm padding gives frame counts that are odd / even-but-not-a-multiple-of-4 /
+    a multiple of 4 only (L = 129 / 130 / 132): the scalar and float2 paths of every kernel the original model uses."""
+    kw = dict(out_channels=64, in_channels=128, num_blocks=2, upsampling_depth=depth,
+              enc_kernel_size=21, enc_num_basis=64, num_sources=2)
+    cfg = O.Config(variant="original", **kw)
+    sd = O.make_state_dict(cfg, seed=8)
+    m = build("original", kw, sd)
+    x = torch.randn(2, 1, T, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    assert max(O.parity_errors(y, O.forward(cfg, sd, x))) < 1e-4
